@@ -1,0 +1,398 @@
+"""akaze_rust_b200 -- host-side mirror of the akaze-rust public API over the B200 C ABI.
+
+The product is libakaze_b200.so (CUDA sm_100a, include/akaze_b200.h). This module is the thin host layer
+a Rust `ffi.rs` would be, written in Python because this image has no Rust toolchain.
+It mirrors the reference interface for the hot path:
+
+    akaze::extract_features(path, Config) -> (evolutions, keypoints, descriptors)   akaze/src/lib.rs:167
+    akaze::match_features(kp0, d0, kp1, d1, lowes_ratio, trials, eps) -> matches     akaze/src/lib.rs:252
+    akaze::types::evolution::Config (+ Default)                                      types/evolution.rs:8-55
+    akaze::ops::feature_matching::descriptor_match                                    ops/feature_matching.rs:23
+
+There is NO CPU fallback: if the shared library is missing or no B200 is present every call raises.
+Nothing in this package imports oracle/ (the CPU restatement is test infrastructure only).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libakaze_b200.so")
+
+DESCRIPTOR_STRIDE = 64
+AKZ_KEEP_EVOLUTIONS = 1
+
+IMAGE_KINDS = {"Lt": 0, "Lsmooth": 1, "Lx": 2, "Ly": 3, "Lxx": 4, "Lyy": 5, "Lxy": 6, "Lflow": 7,
+               "Lstep": 8, "Ldet": 9}
+
+KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("response", "<f4"), ("size", "<f4"),
+                           ("octave", "<u4"), ("class_id", "<u4"), ("angle", "<f4")])
+TOP2_DTYPE = np.dtype([("best_idx", "<u4"), ("best", "<u2"), ("second", "<u2")])
+MATCH_DTYPE = np.dtype([("index_0", "<u8"), ("index_1", "<u8"), ("distance", "<f8")])
+
+
+class AkazeError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("akaze_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+class Config(C.Structure):
+    """types::evolution::Config, field for field (akaze/src/types/evolution.rs:8-38)."""
+    _fields_ = [
+        ("num_sublevels", C.c_uint32),
+        ("max_octave_evolution", C.c_uint32),
+        ("base_scale_offset", C.c_double),
+        ("initial_contrast", C.c_double),
+        ("contrast_percentile", C.c_double),
+        ("contrast_factor_num_bins", C.c_uint64),
+        ("derivative_factor", C.c_double),
+        ("detector_threshold", C.c_double),
+        ("descriptor_channels", C.c_uint64),
+        ("descriptor_pattern_size", C.c_uint64),
+    ]
+
+    @classmethod
+    def default(cls):
+        """Config::default() (evolution.rs:41-54)."""
+        c = cls()
+        _check(lib().akz_default_config(C.byref(c)))
+        return c
+
+    def to_dict(self):
+        return {n: getattr(self, n) for n, _ in self._fields_}
+
+
+class LevelInfo(C.Structure):
+    _fields_ = [("octave", C.c_uint32), ("sublevel", C.c_uint32), ("sigma_size", C.c_uint32),
+                ("width", C.c_uint32), ("height", C.c_uint32), ("n_steps", C.c_uint32),
+                ("esigma", C.c_double), ("etime", C.c_double)]
+
+
+_lib = None
+
+# every symbol include/akaze_b200.h declares
+EXPORTS = [
+    "akz_last_error", "akz_version", "akz_default_config", "akz_create", "akz_destroy", "akz_context_stream",
+    "akz_context_launch_count", "akz_context_set_limits", "akz_extract_u8", "akz_extract_f32",
+    "akz_extract_batch_u8", "akz_extract_batch_u8_device", "akz_context_device_results", "akz_features_count",
+    "akz_features_keypoints", "akz_features_descriptors", "akz_features_descriptor_len",
+    "akz_features_num_levels", "akz_features_level_info", "akz_features_fed_tau",
+    "akz_features_contrast_factor", "akz_features_num_candidates", "akz_features_num_cache",
+    "akz_features_evolution_download", "akz_features_free", "akz_match_top2", "akz_match_top2_device",
+    "akz_merge_top2_device", "akz_descriptor_match",
+]
+
+
+def lib():
+    """Loads libakaze_b200.so; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libakaze_b200.so is missing: run `python __graft_entry__.py` (nvcc, sm_100a) first; "
+                          "there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp = C.c_void_p
+    L.akz_last_error.restype = C.c_char_p
+    L.akz_version.restype = C.c_char_p
+    L.akz_default_config.argtypes = [C.POINTER(Config)]
+    L.akz_create.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(vp)]
+    L.akz_destroy.argtypes = [vp]
+    L.akz_destroy.restype = None
+    L.akz_context_stream.argtypes = [vp]
+    L.akz_context_stream.restype = vp
+    L.akz_context_launch_count.argtypes = [vp]
+    L.akz_context_launch_count.restype = C.c_uint64
+    L.akz_context_set_limits.argtypes = [vp, C.c_uint32, C.c_uint32]
+    L.akz_extract_u8.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_size_t, C.POINTER(Config), C.POINTER(vp)]
+    L.akz_extract_f32.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.POINTER(Config), C.POINTER(vp)]
+    L.akz_extract_batch_u8.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.c_uint32, C.c_uint32, C.c_size_t,
+                                       C.POINTER(Config), C.POINTER(vp)]
+    L.akz_extract_batch_u8_device.argtypes = [vp, C.c_uint32, vp, C.c_uint32, C.c_uint32, C.c_size_t,
+                                              C.POINTER(Config), C.POINTER(C.c_uint32)]
+    L.akz_context_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_uint32)]
+    L.akz_features_count.argtypes = [vp]
+    L.akz_features_count.restype = C.c_uint64
+    L.akz_features_keypoints.argtypes = [vp]
+    L.akz_features_keypoints.restype = vp
+    L.akz_features_descriptors.argtypes = [vp]
+    L.akz_features_descriptors.restype = vp
+    L.akz_features_descriptor_len.argtypes = [vp]
+    L.akz_features_descriptor_len.restype = C.c_uint32
+    L.akz_features_num_levels.argtypes = [vp]
+    L.akz_features_num_levels.restype = C.c_uint32
+    L.akz_features_level_info.argtypes = [vp, C.c_uint32, C.POINTER(LevelInfo)]
+    L.akz_features_fed_tau.argtypes = [vp, C.c_uint32, C.POINTER(C.c_double), C.c_uint32]
+    L.akz_features_contrast_factor.argtypes = [vp]
+    L.akz_features_contrast_factor.restype = C.c_double
+    L.akz_features_num_candidates.argtypes = [vp]
+    L.akz_features_num_candidates.restype = C.c_uint64
+    L.akz_features_num_cache.argtypes = [vp]
+    L.akz_features_num_cache.restype = C.c_uint64
+    L.akz_features_evolution_download.argtypes = [vp, C.c_uint32, C.c_int, vp]
+    L.akz_features_free.argtypes = [vp]
+    L.akz_features_free.restype = None
+    L.akz_match_top2.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint32, C.c_size_t, vp]
+    L.akz_match_top2_device.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint32, vp]
+    L.akz_merge_top2_device.argtypes = [vp, vp, C.c_uint32, C.c_uint64, vp]
+    L.akz_descriptor_match.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint32, C.c_size_t, C.c_uint64,
+                                       C.c_double, vp, C.POINTER(C.c_uint64)]
+    _lib = L
+    return L
+
+
+def _check(rc):
+    if rc != 0:
+        raise AkazeError(rc, lib().akz_last_error().decode("utf-8", "replace"))
+
+
+class EvolutionStep:
+    """Mirror of types::evolution::EvolutionStep (evolution.rs:59-92); images are downloaded lazily
+    from the device (only on an Engine created with keep_evolutions=True)."""
+
+    def __init__(self, features, level, info, taus):
+        self._f = features
+        self._level = level
+        self.etime = info.etime
+        self.esigma = info.esigma
+        self.octave = info.octave
+        self.sublevel = info.sublevel
+        self.sigma_size = info.sigma_size
+        self.width = info.width
+        self.height = info.height
+        self.fed_tau_steps = taus
+
+    def image(self, kind):
+        return self._f.evolution(self._level, kind)
+
+    def __getattr__(self, name):
+        if name in IMAGE_KINDS:
+            return self.image(name)
+        raise AttributeError(name)
+
+
+class Features:
+    """Owns one akz_features handle: keypoints, descriptors and (optionally) the evolutions."""
+
+    def __init__(self, handle):
+        L = lib()
+        self._h = handle
+        n = L.akz_features_count(handle)
+        self.descriptor_len = L.akz_features_descriptor_len(handle)
+        if n:
+            kp = (C.c_uint8 * (n * KEYPOINT_DTYPE.itemsize)).from_address(L.akz_features_keypoints(handle))
+            self.keypoints = np.frombuffer(kp, KEYPOINT_DTYPE).copy()
+            d = (C.c_uint8 * (n * DESCRIPTOR_STRIDE)).from_address(L.akz_features_descriptors(handle))
+            self.descriptors_padded = np.frombuffer(d, np.uint8).reshape(n, DESCRIPTOR_STRIDE).copy()
+        else:
+            self.keypoints = np.zeros(0, KEYPOINT_DTYPE)
+            self.descriptors_padded = np.zeros((0, DESCRIPTOR_STRIDE), np.uint8)
+        # Descriptor.vector of the reference has (162*channels+7)/8 bytes (descriptors.rs:42-46)
+        self.descriptors = self.descriptors_padded[:, :self.descriptor_len]
+        self.contrast_factor = L.akz_features_contrast_factor(handle)
+        self.num_candidates = L.akz_features_num_candidates(handle)
+        self.num_cache = L.akz_features_num_cache(handle)
+        self.evolutions = []
+        for lv in range(L.akz_features_num_levels(handle)):
+            info = LevelInfo()
+            _check(L.akz_features_level_info(handle, lv, C.byref(info)))
+            taus = np.zeros(info.n_steps, np.float64)
+            if info.n_steps:
+                _check(L.akz_features_fed_tau(handle, lv, taus.ctypes.data_as(C.POINTER(C.c_double)), info.n_steps))
+            self.evolutions.append(EvolutionStep(self, lv, info, taus))
+
+    def evolution(self, level, kind):
+        k = IMAGE_KINDS[kind] if isinstance(kind, str) else int(kind)
+        ev = self.evolutions[level]
+        out = np.empty((ev.height, ev.width), np.float32)
+        _check(lib().akz_features_evolution_download(self._h, level, k, out.ctypes.data))
+        return out
+
+    def close(self):
+        if self._h:
+            lib().akz_features_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def _pad64(d):
+    d = np.ascontiguousarray(d, np.uint8)
+    if d.ndim != 2:
+        raise ValueError("descriptors must be a 2-D uint8 array")
+    return d
+
+
+class Engine:
+    """One akz_context: a B200 engine bound to a device (akz_create / akz_destroy)."""
+
+    def __init__(self, device=0, max_width=4096, max_height=4096, max_batch=1, keep_evolutions=False,
+                 max_candidates=None, max_keypoints=None):
+        L = lib()
+        h = C.c_void_p()
+        _check(L.akz_create(device, max_width, max_height, max_batch, AKZ_KEEP_EVOLUTIONS if keep_evolutions else 0,
+                            C.byref(h)))
+        self._h = h
+        self.device = device
+        if max_candidates or max_keypoints:
+            _check(L.akz_context_set_limits(h, max_candidates or 262144, max_keypoints or 65536))
+
+    # -- housekeeping
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().akz_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def stream(self):
+        """cudaStream_t the engine launches on (int), e.g. for torch.cuda.ExternalStream."""
+        return lib().akz_context_stream(self._h)
+
+    @property
+    def launch_count(self):
+        return lib().akz_context_launch_count(self._h)
+
+    # -- extraction
+    def extract_u8(self, gray, config=None):
+        gray = np.ascontiguousarray(gray, np.uint8)
+        cfg = config or Config.default()
+        out = C.c_void_p()
+        _check(lib().akz_extract_u8(self._h, gray.ctypes.data, gray.shape[1], gray.shape[0], gray.strides[0],
+                                    C.byref(cfg), C.byref(out)))
+        return Features(out)
+
+    def extract_f32(self, unit_gray, config=None):
+        img = np.ascontiguousarray(unit_gray, np.float32)
+        cfg = config or Config.default()
+        out = C.c_void_p()
+        _check(lib().akz_extract_f32(self._h, img.ctypes.data, img.shape[1], img.shape[0], C.byref(cfg), C.byref(out)))
+        return Features(out)
+
+    def extract_batch_u8(self, grays, config=None):
+        grays = [np.ascontiguousarray(g, np.uint8) for g in grays]
+        n = len(grays)
+        h, w = grays[0].shape
+        if any(g.shape != (h, w) for g in grays):
+            raise ValueError("all images of a batch must have the same size")
+        cfg = config or Config.default()
+        ptrs = (C.c_void_p * n)(*[g.ctypes.data for g in grays])
+        outs = (C.c_void_p * n)()
+        _check(lib().akz_extract_batch_u8(self._h, n, ptrs, w, h, w, C.byref(cfg), outs))
+        return [Features(C.c_void_p(o)) for o in outs]
+
+    def extract_batch_u8_device(self, d_ptr, n, width, height, stride=None, config=None):
+        """Images already in device memory (n*height*stride bytes); returns per-image keypoint counts."""
+        cfg = config or Config.default()
+        counts = (C.c_uint32 * n)()
+        _check(lib().akz_extract_batch_u8_device(self._h, n, C.c_void_p(d_ptr), width, height, stride or width,
+                                                 C.byref(cfg), counts))
+        return np.frombuffer(counts, np.uint32).copy()
+
+    def device_results(self):
+        kp, ds, cap = C.c_void_p(), C.c_void_p(), C.c_uint32()
+        _check(lib().akz_context_device_results(self._h, C.byref(kp), C.byref(ds), C.byref(cap)))
+        return kp.value, ds.value, cap.value
+
+    # -- matching
+    def match_top2(self, q, db, desc_len=None):
+        """Raw brute-force top-2 (feature_matching.rs:37-50); returns a TOP2_DTYPE array."""
+        q, db = _pad64(q), _pad64(db)
+        stride = q.shape[1]
+        if db.shape[0] and db.shape[1] != stride:
+            raise ValueError("query and database descriptors must have the same row length")
+        desc_len = desc_len or min(stride, DESCRIPTOR_STRIDE)
+        out = np.zeros(q.shape[0], TOP2_DTYPE)
+        _check(lib().akz_match_top2(self._h, q.ctypes.data, q.shape[0], db.ctypes.data, db.shape[0], desc_len, stride,
+                                    out.ctypes.data))
+        return out
+
+    def match_top2_device(self, d_q, nq, d_db, ndb, d_out, db_index_base=0):
+        _check(lib().akz_match_top2_device(self._h, C.c_void_p(d_q), nq, C.c_void_p(d_db), ndb, db_index_base,
+                                           C.c_void_p(d_out)))
+
+    def merge_top2_device(self, d_parts, n_parts, nq, d_out):
+        _check(lib().akz_merge_top2_device(self._h, C.c_void_p(d_parts), n_parts, nq, C.c_void_p(d_out)))
+
+    def descriptor_match(self, d0, d1, distance_threshold=10000, lowes_ratio=0.86, desc_len=None):
+        """ops::feature_matching::descriptor_match (feature_matching.rs:23-94)."""
+        d0, d1 = _pad64(d0), _pad64(d1)
+        stride = d0.shape[1]
+        desc_len = desc_len or min(stride, DESCRIPTOR_STRIDE)
+        out = np.zeros(max(d0.shape[0], 1), MATCH_DTYPE)
+        n = C.c_uint64()
+        _check(lib().akz_descriptor_match(self._h, d0.ctypes.data, d0.shape[0], d1.ctypes.data, d1.shape[0], desc_len,
+                                          stride, distance_threshold, lowes_ratio, out.ctypes.data, C.byref(n)))
+        return out[:n.value].copy()
+
+
+# ---- module-level mirror of the crate's two public functions ----------------------------------------
+_default_engine = None
+
+
+def default_engine(keep_evolutions=True):
+    global _default_engine
+    if _default_engine is None:
+        _default_engine = Engine(0, 8192, 8192, 1, keep_evolutions=keep_evolutions)
+    return _default_engine
+
+
+def to_luma_u8(rgb):
+    """DynamicImage::to_luma of the `image` crate (^0.21): Rec.709 weights in f32, truncating cast.
+    Third-party arithmetic that is not under /root/reference -- parity unpinned, and outside the
+    drop-in boundary (the engine starts at the gray image)."""
+    rgb = np.asarray(rgb)
+    if rgb.ndim == 2:
+        return rgb.astype(np.uint8)
+    r = rgb[..., 0].astype(np.float32)
+    g = rgb[..., 1].astype(np.float32)
+    b = rgb[..., 2].astype(np.float32)
+    lum = np.float32(0.2126) * r + np.float32(0.7152) * g + np.float32(0.0722) * b
+    return lum.astype(np.uint8)
+
+
+def load_gray(path):
+    """image::open + to_luma (lib.rs:171, image.rs:128) on the host."""
+    from PIL import Image
+    with Image.open(path) as im:
+        return to_luma_u8(np.asarray(im.convert("RGB")))
+
+
+def extract_features(input_image_path, options=None, engine=None):
+    """akaze::extract_features (lib.rs:167-194): returns (evolutions, keypoints, descriptors)."""
+    eng = engine or default_engine()
+    gray = load_gray(input_image_path)
+    f = eng.extract_u8(gray, options or Config.default())
+    return f.evolutions, f.keypoints, f.descriptors
+
+
+def descriptor_match(descriptors_0, descriptors_1, distance_threshold=10000, lowes_ratio=0.86, engine=None):
+    eng = engine or default_engine()
+    return eng.descriptor_match(descriptors_0, descriptors_1, distance_threshold, lowes_ratio)
+
+
+def match_features(keypoints_0, descriptors_0, keypoints_1, descriptors_1, lowes_ratio, ransac_trials,
+                   ransac_epsilon_inliers, engine=None, seed=None):
+    """akaze::match_features (lib.rs:252-275): brute-force matching on the GPU, then the reference's
+    RANSAC outlier removal on the host (remove_outliers stays host code)."""
+    from . import ransac
+    output = descriptor_match(descriptors_0, descriptors_1, 10000, lowes_ratio, engine=engine)
+    return ransac.remove_outliers(keypoints_0, keypoints_1, output, ransac_trials, 0.05, ransac_epsilon_inliers,
+                                  seed=seed)

@@ -1,0 +1,765 @@
+// akaze_api.cu -- C ABI (include/akaze_b200.h), level-table construction and launch orchestration.
+//
+// Host-side restatement of the reference's tiny scalar set-up code (all f64/f32 exactly as written):
+//   Config::default                 akaze/src/types/evolution.rs:41-54
+//   EvolutionStep::new              akaze/src/types/evolution.rs:101-126
+//   allocate_evolutions             akaze/src/types/evolution.rs:135-161
+//   fed_tau_by_process_time ...     akaze/src/ops/fed_tau.rs:27-106
+//   gaussian / gaussian_kernel      akaze/src/types/image.rs:341-365
+//   scharr_main_axis_kernel         akaze/src/ops/derivatives.rs:91-101
+// and the orchestration of create_nonlinear_scale_space / find_image_keypoints / extract_features
+// (akaze/src/lib.rs:49-194) as a fixed sequence of kernel launches on one stream.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <memory>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace akz {
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char* what) {
+    return fail(AKZ_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t e__ = (call);                             \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+// ---- FED schedule (fed_tau.rs) -------------------------------------------------------------------
+static bool is_prime(uint64_t n) {
+    if (n < 2) return false;
+    for (uint64_t d = 2; d * d <= n; d++)
+        if (n % d == 0) return false;
+    return true;
+}
+
+// fed_tau.rs:61-106 with reordering = true
+static bool fed_tau_internal(size_t n, double scale, double tau_max, std::vector<double>* tau) {
+    tau->assign(n, 0.0);
+    if (n == 0) return true;
+    std::vector<double> tauh(n);
+    const double c = 1.0 / (4.0 * (double)n + 2.0);
+    const double d = scale * tau_max / 2.0;
+    const double pi = 3.14159265358979323846264338327950288;
+    for (size_t k = 0; k < n; k++) {
+        const double h = cos(pi * (2.0 * (double)k + 1.0) * c);
+        tauh[k] = d / (h * h);
+    }
+    const size_t kappa = n / 2;
+    if (kappa == 0) return false;  // n == 1: the reference underflows and never terminates (Q12)
+    size_t prime = n + 1;
+    while (!is_prime(prime)) prime += 1;
+    size_t k = 0;
+    for (size_t t = 0; t < n; t++) {
+        // usize arithmetic of the reference: a product that is a multiple of `prime` wraps to
+        // usize::MAX and is skipped by `index >= n`
+        size_t m = ((k + 1) * kappa) % prime;
+        while (m == 0 || m - 1 >= n) {
+            k += 1;
+            m = ((k + 1) * kappa) % prime;
+        }
+        (*tau)[t] = tauh[m - 1];
+        k += 1;
+    }
+    return true;
+}
+
+// fed_tau.rs:27-49
+static bool fed_tau_by_process_time(double T, int M, double tau_max, std::vector<double>* tau) {
+    const double t = T / (double)M;
+    const double nf = ceil(sqrt(3.0 * t / tau_max + 0.25) - 0.5 - 1.0e-8) + 0.5;
+    const size_t n = nf > 0.0 ? (size_t)nf : 0;
+    const double scale = 3.0 * t / (tau_max * (double)(n * (n + 1)));
+    return fed_tau_internal(n, scale, tau_max, tau);
+}
+
+// image.rs:341-365, f32 throughout
+static void gaussian_kernel(float r, int size, float* k) {
+    const int hw = size / 2;
+    const float pi = 3.14159265358979323846f;
+    float sum = 0.0f;
+    for (int i = -hw; i <= hw; i++) {
+        const float x = (float)i;
+        const float a = 1.0f / (sqrtf(2.0f * pi) * r);
+        const float v = a * expf(-(x * x) / (2.0f * (r * r)));
+        k[i + hw] = v;
+        sum += v;
+    }
+    for (int i = 0; i < size; i++) k[i] /= sum;
+}
+
+std::string build_plan(uint32_t w, uint32_t h, const akz_config& cfg, Plan* P) {
+    if (cfg.num_sublevels == 0 || cfg.max_octave_evolution == 0) return "num_sublevels and max_octave_evolution must be >= 1";
+    if ((uint64_t)cfg.num_sublevels * cfg.max_octave_evolution > (uint64_t)kMaxLevels) return "too many evolution levels (max 32)";
+    if (cfg.descriptor_channels < 1 || cfg.descriptor_channels > 3) return "descriptor_channels must be 1, 2 or 3";
+    if (cfg.contrast_factor_num_bins < 1 || cfg.contrast_factor_num_bins > (uint64_t)kMaxBins) return "contrast_factor_num_bins must be in 1..1024";
+    if (!(cfg.base_scale_offset > 0.0) || cfg.base_scale_offset > 4.0) return "base_scale_offset must be in (0, 4]";
+    if (w < 64 || h < 32) return "image must be at least 64x32";
+    if (cfg.descriptor_pattern_size < 2 || cfg.descriptor_pattern_size > 64) return "descriptor_pattern_size must be in 2..64";
+    {
+        const float pf = (float)cfg.descriptor_pattern_size;
+        const int p = (int)cfg.descriptor_pattern_size;
+        const int s0 = (int)ceilf(pf * 1.0f), s1 = (int)ceilf(pf * (2.0f / 3.0f)), s2 = (int)ceilf(pf * (1.0f / 2.0f));
+        const int n0 = (2 * p + s0 - 1) / s0, n1 = (2 * p + s1 - 1) / s1, n2 = (2 * p + s2 - 1) / s2;
+        if (n0 != 2 || n1 != 3 || n2 != 4) return "descriptor_pattern_size does not give the 2x2/3x3/4x4 MLDB grids";
+    }
+    P->w = w;
+    P->h = h;
+    P->cfg = cfg;
+    PlanDev& D = P->dev;
+    memset(&D, 0, sizeof(D));
+    P->host.clear();
+
+    // evolution.rs:135-150
+    for (uint32_t i = 0; i < cfg.max_octave_evolution; i++) {
+        const double rfactor = 1.0 / pow(2.0, (double)i);
+        const uint32_t level_height = (uint32_t)((double)h * rfactor);
+        const uint32_t level_width = (uint32_t)((double)w * rfactor);
+        if ((level_width >= 80 && level_height >= 40) || i == 0) {
+            for (uint32_t j = 0; j < cfg.num_sublevels; j++) {
+                LevelHost lh;
+                // evolution.rs:101-113
+                const double esigma = cfg.base_scale_offset * pow(2.0, (double)j / (double)cfg.num_sublevels + (double)i);
+                lh.info.esigma = esigma;
+                lh.info.etime = 0.5 * (esigma * esigma);
+                lh.info.octave = i;
+                lh.info.sublevel = j;
+                lh.info.sigma_size = (uint32_t)round(esigma);
+                lh.info.n_steps = 0;
+                // image.rs:103-104 applied once per octave: floor halving
+                lh.info.width = w >> i;
+                lh.info.height = h >> i;
+                P->host.push_back(lh);
+            }
+        } else {
+            break;
+        }
+    }
+    const int nl = (int)P->host.size();
+    // evolution.rs:151-153
+    for (int i = 1; i < nl; i++) {
+        const double ttime = P->host[i].info.etime - P->host[i - 1].info.etime;
+        if (!fed_tau_by_process_time(ttime, 1, 0.25, &P->host[i].tau)) return "FED schedule with a single step (the reference does not terminate on it)";
+        if (P->host[i].tau.size() > (size_t)kMaxFedSteps) return "too many FED steps per level";
+        P->host[i].info.n_steps = (uint32_t)P->host[i].tau.size();
+        P->host[i].half_tau.clear();
+        for (double t : P->host[i].tau) P->host[i].half_tau.push_back(0.5f * (float)t);  // nonlinear_diffusion.rs:67
+    }
+
+    // filter taps
+    {
+        const float r0 = (float)cfg.base_scale_offset;  // lib.rs:56
+        const int size0 = (int)ceilf(r0) * 2 + 1;       // image.rs:376
+        if (size0 > kMaxGaussTaps) return "base_scale_offset too large";
+        P->gauss0_n = size0;
+        gaussian_kernel(r0, size0, P->gauss0);
+        gaussian_kernel(1.0f, 3, P->gauss1);
+        for (int s = 1; s <= kMaxDetScale; s++) {
+            const double wgt = 10.0 / 3.0;  // derivatives.rs:94-99
+            const double norm = 1.0 / (2.0 * (double)s * (wgt + 2.0));
+            P->sch_n[s] = (float)norm;
+            P->sch_wn[s] = (float)(wgt * norm);
+        }
+        P->sch_n[0] = P->sch_wn[0] = 0.0f;
+    }
+
+    D.n_levels = nl;
+    D.w0 = (int)w;
+    D.h0 = (int)h;
+    D.channels = (int)cfg.descriptor_channels;
+    D.pattern_size = (int)cfg.descriptor_pattern_size;
+    D.desc_len = (int)((162 * cfg.descriptor_channels + 7) / 8);
+    D.n_bins = (int)cfg.contrast_factor_num_bins;
+    D.det_threshold = (float)cfg.detector_threshold;
+    D.percentile = cfg.contrast_percentile;
+    unsigned long long off = 0, moff = 0;
+    const float smax = 10.0f * sqrtf(2.0f);  // scale_space_extrema.rs:14
+    for (int l = 0; l < nl; l++) {
+        LevelDev& lv = D.lv[l];
+        const akz_level_info& in = P->host[l].info;
+        lv.w = (int)in.width;
+        lv.h = (int)in.height;
+        if (lv.w < 64 || lv.h < 32) return "evolution level smaller than one tile (64x32)";
+        lv.octave = (int)in.octave;
+        // detector_response.rs:22-24
+        const double ratio_d = pow(2.0, (double)in.octave);
+        const double sd = round(in.esigma * cfg.derivative_factor / ratio_d);
+        if (!(sd >= 1.0) || sd > (double)kMaxDetScale) return "detector Scharr scale out of range 1..6 (derivative_factor / scale settings)";
+        lv.s_det = (int)sd;
+        lv.wpr = (lv.w + 31) / 32;
+        lv.new_octave = (l > 0 && P->host[l].info.octave > P->host[l - 1].info.octave) ? 1 : 0;
+        lv.n_steps = (int)in.n_steps;
+        lv.ratio = powf(2.0f, (float)in.octave);                        // scale_space_extrema.rs:51
+        lv.kp_size = (float)(in.esigma * cfg.derivative_factor);        // :45
+        lv.size_sq = lv.kp_size * lv.kp_size;                           // :66
+        lv.s_smp = roundf(0.5f * lv.kp_size / lv.ratio);                // :280, descriptors.rs:52
+        lv.half_ratio_m1 = 0.5f * (lv.ratio - 1.0f);                    // :90
+        // is_out (:80-87) evaluated per coordinate with the reference's own f32 expressions
+        const float sigma_size = roundf(lv.kp_size / lv.ratio);         // :52
+        lv.xmin = lv.w;
+        lv.xmax = -1;
+        for (int x = 1; x < lv.w - 1; x++) {
+            const float left_x = roundf((float)x - smax * sigma_size) - 1.0f;
+            const float right_x = roundf((float)x + smax * sigma_size) + 1.0f;
+            if (!(left_x < 0.0f || right_x >= (float)lv.w)) {
+                lv.xmin = std::min(lv.xmin, x);
+                lv.xmax = std::max(lv.xmax, x);
+            }
+        }
+        lv.ymin = lv.h;
+        lv.ymax = -1;
+        for (int y = 1; y < lv.h - 1; y++) {
+            const float up_y = roundf((float)y - smax * sigma_size) - 1.0f;
+            const float down_y = roundf((float)y + smax * sigma_size) + 1.0f;
+            if (!(up_y < 0.0f || down_y >= (float)lv.h)) {
+                lv.ymin = std::min(lv.ymin, y);
+                lv.ymax = std::max(lv.ymax, y);
+            }
+        }
+        lv.off = off;
+        lv.mask_off = moff;
+        off += (unsigned long long)lv.w * lv.h;
+        moff += (unsigned long long)lv.wpr * lv.h;
+    }
+    D.plane_px = off;
+    D.mask_words = moff;
+
+    // orientation windows (scale_space_extrema.rs:300-319): which windows contain atan2(v,v), v > 0
+    {
+        const float PI = 3.14159265358979323846f;
+        const float ang = atan2f(1.0f, 1.0f);
+        float ang1 = 0.0f;
+        int wi = 0;
+        unsigned long long m = 0;
+        while (ang1 < 2.0f * PI) {
+            const float ang2 = (ang1 + PI / 3.0f > 2.0f * PI) ? (ang1 - 5.0f * PI / 3.0f) : (ang1 + PI / 3.0f);
+            ang1 += 0.15f;
+            const bool in = (ang1 < ang2 && ang1 < ang && ang < ang2) ||
+                            (ang2 < ang1 && ((ang > 0.0f && ang < ang2) || (ang > ang1 && ang < 2.0f * PI)));
+            if (in && wi < 64) m |= 1ull << wi;
+            wi++;
+        }
+        if (wi > 64) return "internal: too many orientation windows";
+        D.orient_window_mask = m;
+        D.n_orient_windows = wi;
+    }
+    // dedup hash grid: cells of 16 px (32 px for very large images)
+    D.grid_shift = 4;
+    while ((((int)w >> D.grid_shift) + 1) * (((int)h >> D.grid_shift) + 1) > (1 << 17)) D.grid_shift++;
+    D.grid_w = ((int)w >> D.grid_shift) + 1;
+    D.grid_h = ((int)h >> D.grid_shift) + 1;
+    return "";
+}
+
+}  // namespace akz
+
+using namespace akz;
+
+// ---- context -----------------------------------------------------------------------------------
+struct akz_context {
+    int device = 0;
+    uint32_t max_w = 0, max_h = 0, max_batch = 0, flags = 0;
+    uint32_t cand_cap = 262144, kp_cap = 65536;
+    cudaStream_t stream = nullptr;
+    uint64_t launches = 0;
+    uint64_t generation = 0;
+    bool have_plan = false;
+    Plan plan;
+    Buffers buf;
+    int alloc_batch = 0;           // batch the buffers are sized for
+    std::vector<void*> allocs;     // everything in buf
+    int cur_batch = 0;
+    // matcher scratch
+    void* m_q = nullptr;
+    void* m_db = nullptr;
+    void* m_parts = nullptr;
+    void* m_out = nullptr;
+    size_t m_q_cap = 0, m_db_cap = 0, m_parts_cap = 0, m_out_cap = 0;
+};
+
+struct akz_features {
+    akz_context* ctx = nullptr;
+    uint64_t generation = 0;
+    int img = 0, batch = 0;
+    std::vector<akz_keypoint> kps;
+    std::vector<uint8_t> desc;
+    std::vector<LevelHost> levels;
+    uint32_t desc_len = 0;
+    double contrast = 0.0;
+    uint64_t n_cand = 0, n_cache = 0;
+};
+
+static void free_buffers(akz_context* c) {
+    for (void* p : c->allocs) cudaFree(p);
+    c->allocs.clear();
+    c->buf = Buffers();
+    c->alloc_batch = 0;
+}
+
+template <class T>
+static cudaError_t dalloc(akz_context* c, T** p, size_t count) {
+    void* v = nullptr;
+    cudaError_t e = cudaMalloc(&v, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return e;
+    c->allocs.push_back(v);
+    *p = (T*)v;
+    return cudaSuccess;
+}
+
+static int ensure_buffers(akz_context* c, int batch, bool plan_changed) {
+    if (!plan_changed && batch <= c->alloc_batch) return AKZ_OK;
+    free_buffers(c);
+    const Plan& P = c->plan;
+    Buffers& B = c->buf;
+    const size_t nb = (size_t)batch;
+    const size_t plane = (size_t)P.dev.plane_px * nb;
+    const size_t n0 = (size_t)P.w * P.h * nb;
+    B.keep = (c->flags & AKZ_KEEP_EVOLUTIONS) != 0;
+    CK(dalloc(c, &B.Lt, plane));
+    CK(dalloc(c, &B.Lx, plane));
+    CK(dalloc(c, &B.Ly, plane));
+    CK(dalloc(c, &B.Ldet, plane));
+    CK(dalloc(c, &B.Lsmooth, B.keep ? plane : n0));
+    CK(dalloc(c, &B.Lflow, B.keep ? plane : n0));
+    CK(dalloc(c, &B.Ltmp, n0));
+    if (B.keep) {
+        CK(dalloc(c, &B.Lxx, plane));
+        CK(dalloc(c, &B.Lyy, plane));
+        CK(dalloc(c, &B.Lxy, plane));
+        CK(dalloc(c, &B.Lstep, plane));
+        CK(cudaMemset(B.Lstep, 0, plane * sizeof(float)));
+    }
+    CK(dalloc(c, &B.in_u8, n0));
+    CK(dalloc(c, &B.in_f32, n0));
+    CK(dalloc(c, &B.hmax_bits, nb));
+    CK(dalloc(c, &B.hist, nb * kMaxBins));
+    CK(dalloc(c, &B.kcontrast, nb * kMaxLevels));
+    CK(dalloc(c, &B.mask, (size_t)P.dev.mask_words * nb));
+    CK(dalloc(c, &B.cand, (size_t)c->cand_cap * nb));
+    size_t total_rows = 0;
+    for (int l = 0; l < P.dev.n_levels; l++) total_rows += P.dev.lv[l].h;
+    CK(dalloc(c, &B.rowcount, total_rows * nb));
+    CK(dalloc(c, &B.cand_level_count, nb * (kMaxLevels + 1)));
+    const size_t kc = (size_t)c->kp_cap * nb;
+    CK(dalloc(c, &B.c_x, kc));
+    CK(dalloc(c, &B.c_y, kc));
+    CK(dalloc(c, &B.c_resp, kc));
+    CK(dalloc(c, &B.r_x, kc));
+    CK(dalloc(c, &B.r_y, kc));
+    CK(dalloc(c, &B.c_cls, kc));
+    CK(dalloc(c, &B.c_next, kc));
+    CK(dalloc(c, &B.grid, nb * 2 * (size_t)P.dev.grid_w * P.dev.grid_h));
+    CK(dalloc(c, &B.n_cache, nb));
+    CK(dalloc(c, &B.n_cand_total, nb));
+    CK(dalloc(c, &B.keep_flag, kc));
+    CK(dalloc(c, &B.n_kp, nb));
+    CK(dalloc(c, &B.err_flags, nb));
+    CK(dalloc(c, &B.kps, kc));
+    CK(dalloc(c, &B.desc, kc * kDescStride));
+    CK(dalloc(c, &B.plan_dev, 1));
+    CK(cudaMemcpy(B.plan_dev, &P.dev, sizeof(PlanDev), cudaMemcpyHostToDevice));
+    c->alloc_batch = batch;
+    return AKZ_OK;
+}
+
+static bool same_cfg(const akz_config& a, const akz_config& b) { return memcmp(&a, &b, sizeof(akz_config)) == 0; }
+
+static int prepare(akz_context* c, uint32_t n, uint32_t w, uint32_t h, const akz_config* cfg) {
+    if (!c || !cfg) return fail(AKZ_ERR_INVALID, "null argument");
+    if (n == 0) return fail(AKZ_ERR_INVALID, "empty batch");
+    if (n > c->max_batch) return fail(AKZ_ERR_CAPACITY, "batch larger than the context's max_batch");
+    if (w > c->max_w || h > c->max_h) return fail(AKZ_ERR_CAPACITY, "image larger than the context's max size");
+    CK(cudaSetDevice(c->device));
+    bool changed = false;
+    if (!c->have_plan || c->plan.w != w || c->plan.h != h || !same_cfg(c->plan.cfg, *cfg)) {
+        akz_config z;
+        memset(&z, 0, sizeof(z));  // normalise struct padding before memcmp-style comparison
+        z.num_sublevels = cfg->num_sublevels;
+        z.max_octave_evolution = cfg->max_octave_evolution;
+        z.base_scale_offset = cfg->base_scale_offset;
+        z.initial_contrast = cfg->initial_contrast;
+        z.contrast_percentile = cfg->contrast_percentile;
+        z.contrast_factor_num_bins = cfg->contrast_factor_num_bins;
+        z.derivative_factor = cfg->derivative_factor;
+        z.detector_threshold = cfg->detector_threshold;
+        z.descriptor_channels = cfg->descriptor_channels;
+        z.descriptor_pattern_size = cfg->descriptor_pattern_size;
+        Plan np;
+        std::string err = build_plan(w, h, z, &np);
+        if (!err.empty()) return fail(AKZ_ERR_INVALID, err);
+        c->plan = np;
+        c->have_plan = true;
+        changed = true;
+    }
+    return ensure_buffers(c, (int)n, changed);
+}
+
+// runs the whole pipeline on inputs already in device memory; results stay on the device
+static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8, size_t in_stride) {
+    const Plan& P = c->plan;
+    const Buffers& B = c->buf;
+    Launch L{c->stream, (int)n, c->cand_cap, c->kp_cap};
+    c->generation++;
+    c->cur_batch = (int)n;
+    CK(cudaMemsetAsync(B.mask, 0, (size_t)P.dev.mask_words * n * sizeof(unsigned int), c->stream));
+    CK(cudaMemsetAsync(B.err_flags, 0, n * sizeof(unsigned int), c->stream));
+    int k = 0;
+    k += launch_level0(L, P, B, d_in, is_u8, in_stride);
+    k += launch_contrast(L, P, B);
+    k += launch_detector(L, P, B, 0);
+    for (int l = 1; l < P.dev.n_levels; l++) {
+        k += launch_prep(L, P, B, l);
+        k += launch_fed(L, P, B, l);
+        k += launch_detector(L, P, B, l);
+    }
+    k += launch_compact(L, P, B);
+    k += launch_dedup(L, P, B);
+    k += launch_finalize(L, P, B);
+    k += launch_descriptors(L, P, B);
+    c->launches += (uint64_t)k;
+    CK(cudaGetLastError());
+    return AKZ_OK;
+}
+
+struct BatchStats {
+    std::vector<unsigned int> n_kp, n_cache, n_cand, err;
+    std::vector<double> kcontrast;
+};
+
+static int fetch_stats(akz_context* c, uint32_t n, BatchStats* s) {
+    const Buffers& B = c->buf;
+    s->n_kp.resize(n);
+    s->n_cache.resize(n);
+    s->n_cand.resize(n);
+    s->err.resize(n);
+    s->kcontrast.resize((size_t)n * kMaxLevels);
+    CK(cudaMemcpyAsync(s->n_kp.data(), B.n_kp, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(s->n_cache.data(), B.n_cache, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(s->n_cand.data(), B.n_cand_total, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(s->err.data(), B.err_flags, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(s->kcontrast.data(), B.kcontrast, (size_t)n * kMaxLevels * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    for (uint32_t i = 0; i < n; i++) {
+        if (s->err[i] & kErrCandOverflow) return fail(AKZ_ERR_CAPACITY, "candidate list overflow (raise max_candidates)");
+        if (s->err[i] & kErrKpOverflow) return fail(AKZ_ERR_CAPACITY, "keypoint cache overflow (raise max_keypoints)");
+        if (s->err[i] & kErrBounds) return fail(AKZ_ERR_BOUNDS, "a descriptor/orientation sample fell outside the image (the reference panics here)");
+    }
+    return AKZ_OK;
+}
+
+static int collect_features(akz_context* c, uint32_t n, akz_features** outs) {
+    BatchStats st;
+    int rc = fetch_stats(c, n, &st);
+    if (rc != AKZ_OK) return rc;
+    const Buffers& B = c->buf;
+    std::vector<std::unique_ptr<akz_features>> fs;
+    for (uint32_t i = 0; i < n; i++) {
+        std::unique_ptr<akz_features> f(new akz_features());
+        f->ctx = c;
+        f->generation = c->generation;
+        f->img = (int)i;
+        f->batch = (int)n;
+        f->levels = c->plan.host;
+        f->desc_len = (uint32_t)c->plan.dev.desc_len;
+        f->contrast = st.kcontrast[(size_t)i * kMaxLevels];
+        f->n_cand = st.n_cand[i];
+        f->n_cache = st.n_cache[i];
+        const size_t nk = st.n_kp[i];
+        f->kps.resize(nk);
+        f->desc.resize(nk * kDescStride);
+        if (nk) {
+            CK(cudaMemcpyAsync(f->kps.data(), B.kps + (size_t)i * c->kp_cap, nk * sizeof(akz_keypoint), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(f->desc.data(), B.desc + (size_t)i * c->kp_cap * kDescStride, nk * kDescStride, cudaMemcpyDeviceToHost, c->stream));
+        }
+        fs.push_back(std::move(f));
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    for (uint32_t i = 0; i < n; i++) outs[i] = fs[i].release();
+    return AKZ_OK;
+}
+
+extern "C" {
+
+const char* akz_last_error(void) { return g_last_error.c_str(); }
+const char* akz_version(void) { return "akaze_b200 0.1 (sm_100a)"; }
+
+int akz_default_config(akz_config* cfg) {
+    if (!cfg) return fail(AKZ_ERR_INVALID, "null config");
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->num_sublevels = 4;
+    cfg->max_octave_evolution = 4;
+    cfg->base_scale_offset = 1.6;
+    cfg->initial_contrast = 0.001;
+    cfg->contrast_percentile = 0.7;
+    cfg->contrast_factor_num_bins = 300;
+    cfg->derivative_factor = 1.5;
+    cfg->detector_threshold = 0.001;
+    cfg->descriptor_channels = 3;
+    cfg->descriptor_pattern_size = 10;
+    return AKZ_OK;
+}
+
+int akz_create(int device, uint32_t max_width, uint32_t max_height, uint32_t max_batch, uint32_t flags, akz_context** out) {
+    if (!out) return fail(AKZ_ERR_INVALID, "null out");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return fail(AKZ_ERR_CUDA, "no CUDA device: this engine has no CPU fallback");
+    if (device < 0 || device >= count) return fail(AKZ_ERR_INVALID, "bad device index");
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(AKZ_ERR_CUDA, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + ", the kernels are built for sm_100a only");
+    if (max_batch == 0 || max_width < 64 || max_height < 32) return fail(AKZ_ERR_INVALID, "max_batch >= 1, max size >= 64x32 required");
+    std::unique_ptr<akz_context> c(new akz_context());
+    c->device = device;
+    c->max_w = max_width;
+    c->max_h = max_height;
+    c->max_batch = max_batch;
+    c->flags = flags;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(init_detector_attributes());
+    *out = c.release();
+    return AKZ_OK;
+}
+
+void akz_destroy(akz_context* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    free_buffers(c);
+    cudaFree(c->m_q);
+    cudaFree(c->m_db);
+    cudaFree(c->m_parts);
+    cudaFree(c->m_out);
+    cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+void* akz_context_stream(akz_context* c) { return c ? (void*)c->stream : nullptr; }
+uint64_t akz_context_launch_count(const akz_context* c) { return c ? c->launches : 0; }
+
+int akz_context_set_limits(akz_context* c, uint32_t max_candidates, uint32_t max_keypoints) {
+    if (!c || max_candidates == 0 || max_keypoints == 0) return fail(AKZ_ERR_INVALID, "bad limits");
+    if (max_keypoints > 0x7fffffffu) return fail(AKZ_ERR_INVALID, "max_keypoints too large");
+    if (max_candidates < max_keypoints) max_candidates = max_keypoints;
+    c->cand_cap = max_candidates;
+    c->kp_cap = max_keypoints;
+    cudaSetDevice(c->device);
+    free_buffers(c);
+    return AKZ_OK;
+}
+
+int akz_extract_batch_u8(akz_context* c, uint32_t n, const uint8_t* const* grays, uint32_t w, uint32_t h, size_t stride,
+                         const akz_config* cfg, akz_features** outs) {
+    if (!grays || !outs) return fail(AKZ_ERR_INVALID, "null argument");
+    if (stride < w) return fail(AKZ_ERR_INVALID, "stride < width");
+    int rc = prepare(c, n, w, h, cfg);
+    if (rc != AKZ_OK) return rc;
+    for (uint32_t i = 0; i < n; i++) {
+        if (!grays[i]) return fail(AKZ_ERR_INVALID, "null image");
+        CK(cudaMemcpy2DAsync(c->buf.in_u8 + (size_t)i * w * h, w, grays[i], stride, w, h, cudaMemcpyHostToDevice, c->stream));
+    }
+    rc = run_pipeline(c, n, c->buf.in_u8, true, w);
+    if (rc != AKZ_OK) return rc;
+    return collect_features(c, n, outs);
+}
+
+int akz_extract_u8(akz_context* c, const uint8_t* gray, uint32_t w, uint32_t h, size_t stride, const akz_config* cfg,
+                   akz_features** out) {
+    const uint8_t* p[1] = {gray};
+    return akz_extract_batch_u8(c, 1, p, w, h, stride, cfg, out);
+}
+
+int akz_extract_f32(akz_context* c, const float* unit_gray, uint32_t w, uint32_t h, const akz_config* cfg, akz_features** out) {
+    if (!unit_gray || !out) return fail(AKZ_ERR_INVALID, "null argument");
+    int rc = prepare(c, 1, w, h, cfg);
+    if (rc != AKZ_OK) return rc;
+    CK(cudaMemcpyAsync(c->buf.in_f32, unit_gray, (size_t)w * h * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    rc = run_pipeline(c, 1, c->buf.in_f32, false, w);
+    if (rc != AKZ_OK) return rc;
+    return collect_features(c, 1, out);
+}
+
+int akz_extract_batch_u8_device(akz_context* c, uint32_t n, const void* d_grays, uint32_t w, uint32_t h, size_t stride,
+                                const akz_config* cfg, uint32_t* counts) {
+    if (!d_grays || !counts) return fail(AKZ_ERR_INVALID, "null argument");
+    if (stride < w) return fail(AKZ_ERR_INVALID, "stride < width");
+    int rc = prepare(c, n, w, h, cfg);
+    if (rc != AKZ_OK) return rc;
+    rc = run_pipeline(c, n, d_grays, true, stride);
+    if (rc != AKZ_OK) return rc;
+    BatchStats st;
+    rc = fetch_stats(c, n, &st);
+    if (rc != AKZ_OK) return rc;
+    for (uint32_t i = 0; i < n; i++) counts[i] = st.n_kp[i];
+    return AKZ_OK;
+}
+
+int akz_context_device_results(akz_context* c, void** d_keypoints, void** d_descriptors, uint32_t* kp_capacity) {
+    if (!c || !c->buf.kps) return fail(AKZ_ERR_INVALID, "no extraction has run on this context");
+    if (d_keypoints) *d_keypoints = c->buf.kps;
+    if (d_descriptors) *d_descriptors = c->buf.desc;
+    if (kp_capacity) *kp_capacity = c->kp_cap;
+    return AKZ_OK;
+}
+
+uint64_t akz_features_count(const akz_features* f) { return f ? f->kps.size() : 0; }
+const akz_keypoint* akz_features_keypoints(const akz_features* f) { return f ? f->kps.data() : nullptr; }
+const uint8_t* akz_features_descriptors(const akz_features* f) { return f ? f->desc.data() : nullptr; }
+uint32_t akz_features_descriptor_len(const akz_features* f) { return f ? f->desc_len : 0; }
+uint32_t akz_features_num_levels(const akz_features* f) { return f ? (uint32_t)f->levels.size() : 0; }
+int akz_features_level_info(const akz_features* f, uint32_t level, akz_level_info* out) {
+    if (!f || !out || level >= f->levels.size()) return fail(AKZ_ERR_INVALID, "bad level");
+    *out = f->levels[level].info;
+    return AKZ_OK;
+}
+int akz_features_fed_tau(const akz_features* f, uint32_t level, double* out, uint32_t cap) {
+    if (!f || level >= f->levels.size() || (!out && cap)) return fail(AKZ_ERR_INVALID, "bad level");
+    const std::vector<double>& t = f->levels[level].tau;
+    for (uint32_t i = 0; i < cap && i < t.size(); i++) out[i] = t[i];
+    return AKZ_OK;
+}
+double akz_features_contrast_factor(const akz_features* f) { return f ? f->contrast : 0.0; }
+uint64_t akz_features_num_candidates(const akz_features* f) { return f ? f->n_cand : 0; }
+uint64_t akz_features_num_cache(const akz_features* f) { return f ? f->n_cache : 0; }
+
+int akz_features_evolution_download(const akz_features* f, uint32_t level, int kind, float* dst) {
+    if (!f || !dst || level >= f->levels.size()) return fail(AKZ_ERR_INVALID, "bad argument");
+    akz_context* c = f->ctx;
+    if (!(c->flags & AKZ_KEEP_EVOLUTIONS)) return fail(AKZ_ERR_INVALID, "context was created without AKZ_KEEP_EVOLUTIONS");
+    if (c->generation != f->generation) return fail(AKZ_ERR_INVALID, "evolutions were overwritten by a later extraction");
+    CK(cudaSetDevice(c->device));
+    const Buffers& B = c->buf;
+    const float* plane = nullptr;
+    switch (kind) {
+        case AKZ_LT: plane = B.Lt; break;
+        case AKZ_LSMOOTH: plane = (level == 0) ? B.Lt : B.Lsmooth; break;  // lib.rs:58
+        case AKZ_LX: plane = B.Lx; break;
+        case AKZ_LY: plane = B.Ly; break;
+        case AKZ_LXX: plane = B.Lxx; break;
+        case AKZ_LYY: plane = B.Lyy; break;
+        case AKZ_LXY: plane = B.Lxy; break;
+        case AKZ_LFLOW: plane = B.Lflow; break;
+        case AKZ_LSTEP: plane = B.Lstep; break;
+        case AKZ_LDET: plane = B.Ldet; break;
+        default: return fail(AKZ_ERR_INVALID, "bad image kind");
+    }
+    if (level == 0 && (kind == AKZ_LFLOW || kind == AKZ_LSTEP)) return fail(AKZ_ERR_INVALID, "level 0 has no Lflow/Lstep (0x0 in the reference)");
+    const LevelDev& lv = c->plan.dev.lv[level];
+    const size_t px = (size_t)lv.w * lv.h;
+    const float* src = plane + (size_t)lv.off * f->batch + (size_t)f->img * px;
+    CK(cudaMemcpyAsync(dst, src, px * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return AKZ_OK;
+}
+
+void akz_features_free(akz_features* f) { delete f; }
+
+// ---- matching ------------------------------------------------------------------------------------
+static int grow(void** p, size_t* cap, size_t need) {
+    if (need <= *cap) return AKZ_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    CK(cudaMalloc(p, need));
+    *cap = need;
+    return AKZ_OK;
+}
+
+int akz_match_top2_device(akz_context* c, const void* d_q, uint64_t nq, const void* d_db, uint64_t ndb, uint32_t db_index_base,
+                          void* d_out) {
+    if (!c || (nq && (!d_q || !d_out)) || (ndb && !d_db)) return fail(AKZ_ERR_INVALID, "null argument");
+    if (nq == 0) return AKZ_OK;
+    if (ndb > 0xffffffffull || nq > 0xffffffffull) return fail(AKZ_ERR_CAPACITY, "more than 2^32 descriptors");
+    CK(cudaSetDevice(c->device));
+    const int parts = match_parts(nq, ndb);
+    if (parts == 1) {
+        c->launches += launch_match_top2(c->stream, (const uint8_t*)d_q, nq, (const uint8_t*)d_db, ndb, db_index_base, (akz_top2*)d_out, 1);
+    } else {
+        int rc = grow(&c->m_parts, &c->m_parts_cap, (size_t)parts * nq * sizeof(akz_top2));
+        if (rc != AKZ_OK) return rc;
+        c->launches += launch_match_top2(c->stream, (const uint8_t*)d_q, nq, (const uint8_t*)d_db, ndb, db_index_base, (akz_top2*)c->m_parts, parts);
+        c->launches += launch_merge_top2(c->stream, (const akz_top2*)c->m_parts, (uint32_t)parts, nq, (akz_top2*)d_out);
+    }
+    CK(cudaGetLastError());
+    return AKZ_OK;
+}
+
+int akz_merge_top2_device(akz_context* c, const void* d_parts, uint32_t n_parts, uint64_t nq, void* d_out) {
+    if (!c || (nq && (!d_parts || !d_out)) || n_parts == 0) return fail(AKZ_ERR_INVALID, "bad argument");
+    CK(cudaSetDevice(c->device));
+    c->launches += launch_merge_top2(c->stream, (const akz_top2*)d_parts, n_parts, nq, (akz_top2*)d_out);
+    CK(cudaGetLastError());
+    return AKZ_OK;
+}
+
+// host rows (stride, desc_len) -> device rows of 64 bytes, zero padded
+static int upload_padded(akz_context* c, const uint8_t* src, uint64_t n, uint32_t desc_len, size_t stride, void** dbuf, size_t* cap) {
+    int rc = grow(dbuf, cap, std::max<size_t>((size_t)n * kDescStride, 64));
+    if (rc != AKZ_OK) return rc;
+    if (n == 0) return AKZ_OK;
+    if (stride == (size_t)kDescStride && desc_len == (uint32_t)kDescStride) {
+        CK(cudaMemcpyAsync(*dbuf, src, (size_t)n * kDescStride, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        CK(cudaMemsetAsync(*dbuf, 0, (size_t)n * kDescStride, c->stream));
+        CK(cudaMemcpy2DAsync(*dbuf, kDescStride, src, stride, desc_len, n, cudaMemcpyHostToDevice, c->stream));
+    }
+    return AKZ_OK;
+}
+
+int akz_match_top2(akz_context* c, const uint8_t* q, uint64_t nq, const uint8_t* db, uint64_t ndb, uint32_t desc_len, size_t stride,
+                   akz_top2* out) {
+    if (!c || (nq && (!q || !out)) || (ndb && !db)) return fail(AKZ_ERR_INVALID, "null argument");
+    if (desc_len == 0 || desc_len > (uint32_t)kDescStride || stride < desc_len) return fail(AKZ_ERR_INVALID, "desc_len must be 1..64 and <= stride");
+    if (nq == 0) return AKZ_OK;
+    CK(cudaSetDevice(c->device));
+    int rc = upload_padded(c, q, nq, desc_len, stride, &c->m_q, &c->m_q_cap);
+    if (rc != AKZ_OK) return rc;
+    rc = upload_padded(c, db, ndb, desc_len, stride, &c->m_db, &c->m_db_cap);
+    if (rc != AKZ_OK) return rc;
+    rc = grow(&c->m_out, &c->m_out_cap, (size_t)nq * sizeof(akz_top2));
+    if (rc != AKZ_OK) return rc;
+    rc = akz_match_top2_device(c, c->m_q, nq, c->m_db, ndb, 0, c->m_out);
+    if (rc != AKZ_OK) return rc;
+    CK(cudaMemcpyAsync(out, c->m_out, (size_t)nq * sizeof(akz_top2), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return AKZ_OK;
+}
+
+int akz_descriptor_match(akz_context* c, const uint8_t* d0, uint64_t n0, const uint8_t* d1, uint64_t n1, uint32_t desc_len,
+                         size_t stride, uint64_t distance_threshold, double lowes_ratio, akz_match* out, uint64_t* n_out) {
+    if (!n_out || (n0 && !out)) return fail(AKZ_ERR_INVALID, "null argument");
+    *n_out = 0;
+    if (distance_threshold != 10000) return fail(AKZ_ERR_INVALID, "distance_threshold is hard-wired to 10000 (akaze/src/lib.rs:264)");
+    std::vector<akz_top2> t(n0);
+    int rc = akz_match_top2(c, d0, n0, d1, n1, desc_len, stride, t.data());
+    if (rc != AKZ_OK) return rc;
+    const double r2 = lowes_ratio * lowes_ratio;  // powi(2), feature_matching.rs:61
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < n0; i++) {
+        const uint64_t mn = t[i].best, sc = t[i].second;
+        if ((double)mn < (double)sc * r2) {
+            if (mn < distance_threshold) {
+                out[k].index_0 = i;
+                out[k].index_1 = t[i].best_idx;
+                out[k].distance = (double)mn;
+                k++;
+            }
+        }
+    }
+    *n_out = k;
+    return AKZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,169 @@
+// common.cuh -- shared declarations of the B200 A-KAZE engine (internal; the public ABI is
+// include/akaze_b200.h). All device arithmetic that must match the reference bit for bit is written
+// with explicit __fmul_rn/__fadd_rn-equivalent operation order and the library is compiled with
+// --fmad=false so that nvcc never contracts a*b+c (rustc does not either).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/akaze_b200.h"
+
+namespace akz {
+
+constexpr int kMaxLevels = 32;
+constexpr int kMaxFedSteps = 64;   // per level (default config needs 29)
+constexpr int kMaxGaussTaps = 9;   // base_scale_offset <= 4
+constexpr int kMaxDetScale = 6;    // Scharr scale in the detector (default config needs 4)
+constexpr int kMaxBins = 1024;     // contrast histogram bins (default 300)
+constexpr int kDescStride = AKZ_DESCRIPTOR_STRIDE;
+
+// ---- per-level constants, host + device -------------------------------------------------------
+struct LevelDev {
+    int w, h;             // level size
+    int octave;           // evolution.octave
+    int s_det;            // Scharr scale of the detector (detector_response.rs:22-24)
+    int wpr;              // candidate-mask words per row
+    int xmin, xmax;       // inclusive x range passing the is_out test (scale_space_extrema.rs:80-87)
+    int ymin, ymax;
+    int new_octave;       // level starts a new octave (lib.rs:80)
+    int n_steps;
+    float ratio;          // 2^octave as f32
+    float kp_size;        // (esigma * derivative_factor) as f32
+    float size_sq;        // kp_size * kp_size (f32 product)
+    float s_smp;          // round(0.5 * size / ratio): sample step of orientation and descriptor
+    float half_ratio_m1;  // 0.5f * (ratio - 1.0f)
+    unsigned long long off;       // float offset of this level inside a per-image plane
+    unsigned long long mask_off;  // word offset inside a per-image candidate mask
+};
+
+struct PlanDev {
+    int n_levels;
+    int w0, h0;
+    int channels;          // descriptor_channels
+    int pattern_size;      // descriptor_pattern_size
+    int desc_len;          // (162*channels+7)/8
+    int n_bins;
+    float det_threshold;   // detector_threshold as f32
+    double percentile;
+    unsigned long long plane_px;    // sum of level pixels (per image)
+    unsigned long long mask_words;  // per image
+    unsigned long long orient_window_mask;  // bit w set: sliding window w contains atan2(v,v), v>0
+    int n_orient_windows;
+    int grid_shift;        // dedup hash grid: cell = 1<<grid_shift full-resolution pixels
+    int grid_w, grid_h;
+    LevelDev lv[kMaxLevels];
+};
+
+struct LevelHost {
+    akz_level_info info;
+    std::vector<double> tau;
+    std::vector<float> half_tau;  // 0.5f * (tau as f32)  (nonlinear_diffusion.rs:67)
+};
+
+struct Plan {
+    uint32_t w = 0, h = 0;
+    akz_config cfg{};
+    PlanDev dev{};
+    std::vector<LevelHost> host;
+    float gauss0[kMaxGaussTaps];  // taps of gaussian_blur(image, base_scale_offset)
+    int gauss0_n = 0;
+    float gauss1[3];              // taps of gaussian_blur(.., 1.0)
+    float sch_n[kMaxDetScale + 1], sch_wn[kMaxDetScale + 1];  // Scharr main-axis taps per scale
+};
+
+// builds the level table; returns "" or an error message (host_plan.cpp part of akaze_api.cu)
+std::string build_plan(uint32_t w, uint32_t h, const akz_config& cfg, Plan* out);
+
+// ---- device buffers of one context -------------------------------------------------------------
+struct Buffers {
+    // persistent per batch: [level][image][N_l] inside each plane
+    float* Lt = nullptr;
+    float* Lx = nullptr;
+    float* Ly = nullptr;
+    float* Ldet = nullptr;
+    // per-level scratch (octave-0 sized, per image) unless keep_evolutions
+    float* Lsmooth = nullptr;
+    float* Lflow = nullptr;
+    float* Ltmp = nullptr;
+    // keep_evolutions extras (plane layout)
+    float* Lxx = nullptr;
+    float* Lyy = nullptr;
+    float* Lxy = nullptr;
+    float* Lstep = nullptr;
+    bool keep = false;
+    // input staging
+    uint8_t* in_u8 = nullptr;
+    float* in_f32 = nullptr;
+    // contrast
+    unsigned long long* hmax_bits = nullptr;  // [B] f64 bits (values >= 0 order like u64)
+    unsigned int* hist = nullptr;             // [B][n_bins]
+    double* kcontrast = nullptr;              // [B][kMaxLevels] contrast factor per level
+    // candidates
+    unsigned int* mask = nullptr;       // [B][mask_words]
+    unsigned int* cand = nullptr;       // [B][cand_cap] packed flat index, level-major raster order
+    unsigned int* rowcount = nullptr;   // [B][sum of level heights] scratch of the compaction
+    unsigned int* cand_level_count = nullptr;  // [B][kMaxLevels+1] exclusive offsets per level
+    // dedup cache
+    float* c_x = nullptr;               // [B][kp_cap]
+    float* c_y = nullptr;
+    float* c_resp = nullptr;
+    float* r_x = nullptr;               // [B][kp_cap] refined points (sub-pixel step)
+    float* r_y = nullptr;
+    int* c_cls = nullptr;
+    int* c_next = nullptr;
+    int* grid = nullptr;                // [B][2][grid_cells]
+    unsigned int* n_cache = nullptr;    // [B]
+    unsigned int* n_cand_total = nullptr;  // [B]
+    unsigned int* keep_flag = nullptr;  // [B][kp_cap]
+    unsigned int* n_kp = nullptr;       // [B]
+    unsigned int* err_flags = nullptr;  // [B]
+    akz_keypoint* kps = nullptr;        // [B][kp_cap]
+    uint8_t* desc = nullptr;            // [B][kp_cap][64]
+    PlanDev* plan_dev = nullptr;
+    float* half_tau_dev = nullptr;      // [kMaxLevels][kMaxFedSteps]
+};
+
+enum ErrBits : unsigned int {
+    kErrCandOverflow = 1u,
+    kErrKpOverflow = 2u,
+    kErrBounds = 4u,
+};
+
+// ---- launchers (each returns the number of kernels launched) ---------------------------------
+struct Launch {
+    cudaStream_t stream;
+    int batch;          // images in this launch
+    uint32_t cand_cap;  // per image
+    uint32_t kp_cap;    // per image
+};
+
+// scale_space.cu
+int launch_level0(const Launch& L, const Plan& P, const Buffers& B, const void* d_in, bool is_u8, size_t in_stride);
+int launch_contrast(const Launch& L, const Plan& P, const Buffers& B);
+int launch_prep(const Launch& L, const Plan& P, const Buffers& B, int level);
+int launch_fed(const Launch& L, const Plan& P, const Buffers& B, int level);
+// detector.cu
+cudaError_t init_detector_attributes();
+int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level);
+int launch_compact(const Launch& L, const Plan& P, const Buffers& B);
+// keypoints.cu
+int launch_dedup(const Launch& L, const Plan& P, const Buffers& B);
+int launch_finalize(const Launch& L, const Plan& P, const Buffers& B);
+int launch_descriptors(const Launch& L, const Plan& P, const Buffers& B);
+// matcher.cu
+int match_parts(uint64_t nq, uint64_t ndb);  // how many database parts the grid is split into
+// d_out: akz_top2[n_parts][nq]
+int launch_match_top2(cudaStream_t s, const uint8_t* d_q, uint64_t nq, const uint8_t* d_db, uint64_t ndb,
+                      uint32_t db_index_base, akz_top2* d_out, int n_parts);
+int launch_merge_top2(cudaStream_t s, const akz_top2* d_parts, uint32_t n_parts, uint64_t nq, akz_top2* d_out);
+
+// helpers to address [level][image] slabs
+static inline size_t plane_off(const Plan& P, int batch, int level, int img) {
+    return (size_t)P.dev.lv[level].off * (size_t)batch + (size_t)img * (size_t)P.dev.lv[level].w * P.dev.lv[level].h;
+}
+
+}  // namespace akz

@@ -1,0 +1,327 @@
+// detector.cu -- scale-normalised Hessian determinant and ordered candidate emission.
+//
+// Replaces (reference paths relative to the akaze-rust repository):
+//   compute_multiscale_derivatives / detector_response   akaze/src/ops/detector_response.rs:8-55
+//   the threshold + 4-neighbour test and the is_out test of find_scale_space_extrema
+//                                                        akaze/src/ops/scale_space_extrema.rs:32-42, 80-88
+//
+// Per level, one kernel evaluates the whole derivative chain in shared memory:
+//   Lx  = V_off (H_main(Lsmooth))   "x_order"  (derivatives.rs:41-47; the reference's Lx is d/dy, Q1)
+//   Ly  = V_main(H_off (Lsmooth))   "y_order"  (derivatives.rs:59-65)
+//   Lxx = V_off (H_main(Lx)),  Lyy = V_main(H_off(Ly)),  Lxy = V_main(H_off(Lx))
+//   Ldet = ((Lxx*Lyy) - (Lxy*Lxy)) * (s^4 as f32)
+// with the scaled Scharr taps [n,0..,wn,0..,n] / [-1,0..0,1] applied in tap order; zero taps add an
+// exact +0 and are skipped. Every pass clamps like fill_border (see scale_space.cu). Candidates are
+// written as one bit per pixel; a second set of kernels turns the bitmask into a list in raster order,
+// which the order-dependent cache pass of the reference needs.
+#include "common.cuh"
+
+namespace akz {
+namespace {
+
+constexpr int DT = 32;  // tile edge
+constexpr int NTX = 32, NTY = 8;
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+struct DetParams {
+    int W, H, s;
+    float n, wn;  // scharr_main_axis_kernel(s)
+    float quat;   // (s*s*s*s) as f32
+    float thr;
+    int xmin, xmax, ymin, ymax;
+    int wpr;
+};
+
+__global__ void __launch_bounds__(NTX* NTY)
+k_detector(const float* __restrict__ lsmooth, size_t img_px, float* __restrict__ oLx, float* __restrict__ oLy,
+           float* __restrict__ oLdet, float* __restrict__ oLxx, float* __restrict__ oLyy, float* __restrict__ oLxy,
+           unsigned int* __restrict__ mask, size_t mask_img_words, DetParams p) {
+    extern __shared__ float smem[];
+    const int s = p.s, W = p.W, H = p.H;
+    const int HL = 2 * s + 1;
+    const int PW = DT + 2 * HL;
+    const int N = PW * PW;
+    float* b0 = smem;
+    float* b1 = b0 + N;
+    float* b2 = b1 + N;
+    float* b3 = b2 + N;
+    float* b4 = b3 + N;
+    const int tx0 = min((int)blockIdx.x * DT, W - DT);
+    const int ty0 = min((int)blockIdx.y * DT, H - DT);
+    const int img = blockIdx.z;
+    auto idx = [&](int x, int y) { return (y - ty0 + HL) * PW + (x - tx0 + HL); };
+    const float* L = lsmooth + (size_t)img * img_px;
+
+    {  // stage 0: Lsmooth over tile +- (2s+1)
+        const int xa = max(tx0 - HL, 0), xb = min(tx0 + DT + HL, W);
+        const int ya = max(ty0 - HL, 0), yb = min(ty0 + DT + HL, H);
+        for (int y = ya + threadIdx.y; y < yb; y += NTY)
+            for (int x = xa + threadIdx.x; x < xb; x += NTX) b0[idx(x, y)] = L[(size_t)y * W + x];
+    }
+    __syncthreads();
+    {  // stage 1: A = H_main(L) -> b1, Bo = H_off(L) -> b2 : x in tile+-(s+1), y in tile+-(2s+1)
+        const int xa = max(tx0 - s - 1, 0), xb = min(tx0 + DT + s + 1, W);
+        const int ya = max(ty0 - HL, 0), yb = min(ty0 + DT + HL, H);
+        for (int y = ya + threadIdx.y; y < yb; y += NTY)
+            for (int x = xa + threadIdx.x; x < xb; x += NTX) {
+                const int cx = clampi(x, s, W - 1 - s), cy = clampi(y, s, H - 1 - s);
+                const float l = b0[idx(cx - s, cy)], c = b0[idx(cx, cy)], r = b0[idx(cx + s, cy)];
+                float acc = 0.0f + p.n * l;
+                acc = acc + p.wn * c;
+                acc = acc + p.n * r;
+                b1[idx(x, y)] = acc;
+                b2[idx(x, y)] = r - l;
+            }
+    }
+    __syncthreads();
+    {  // stage 2: Lx = V_off(A) -> b3, Ly = V_main(Bo) -> b4 : tile +- (s+1)
+        const int xa = max(tx0 - s - 1, 0), xb = min(tx0 + DT + s + 1, W);
+        const int ya = max(ty0 - s - 1, 0), yb = min(ty0 + DT + s + 1, H);
+        float* ox = oLx + (size_t)img * img_px;
+        float* oy = oLy + (size_t)img * img_px;
+        for (int y = ya + threadIdx.y; y < yb; y += NTY)
+            for (int x = xa + threadIdx.x; x < xb; x += NTX) {
+                const int cx = clampi(x, s, W - 1 - s), cy = clampi(y, s, H - 1 - s);
+                const float lx = b1[idx(cx, cy + s)] - b1[idx(cx, cy - s)];
+                float acc = 0.0f + p.n * b2[idx(cx, cy - s)];
+                acc = acc + p.wn * b2[idx(cx, cy)];
+                acc = acc + p.n * b2[idx(cx, cy + s)];
+                b3[idx(x, y)] = lx;
+                b4[idx(x, y)] = acc;
+                if (x >= tx0 && x < tx0 + DT && y >= ty0 && y < ty0 + DT) {
+                    ox[(size_t)y * W + x] = lx;
+                    oy[(size_t)y * W + x] = acc;
+                }
+            }
+    }
+    __syncthreads();
+    {  // stage 3: C = H_main(Lx) -> b0, D = H_off(Ly) -> b1, E = H_off(Lx) -> b2 : x tile+-1, y tile+-(s+1)
+        const int xa = max(tx0 - 1, 0), xb = min(tx0 + DT + 1, W);
+        const int ya = max(ty0 - s - 1, 0), yb = min(ty0 + DT + s + 1, H);
+        for (int y = ya + threadIdx.y; y < yb; y += NTY)
+            for (int x = xa + threadIdx.x; x < xb; x += NTX) {
+                const int cx = clampi(x, s, W - 1 - s), cy = clampi(y, s, H - 1 - s);
+                const float l = b3[idx(cx - s, cy)], c = b3[idx(cx, cy)], r = b3[idx(cx + s, cy)];
+                float acc = 0.0f + p.n * l;
+                acc = acc + p.wn * c;
+                acc = acc + p.n * r;
+                b0[idx(x, y)] = acc;
+                b2[idx(x, y)] = r - l;
+                b1[idx(x, y)] = b4[idx(cx + s, cy)] - b4[idx(cx - s, cy)];
+            }
+    }
+    __syncthreads();
+    {  // stage 4: Ldet over tile +- 1 -> b3 (Lx in b3 is dead after stage 3)
+        const int xa = max(tx0 - 1, 0), xb = min(tx0 + DT + 1, W);
+        const int ya = max(ty0 - 1, 0), yb = min(ty0 + DT + 1, H);
+        float* od = oLdet + (size_t)img * img_px;
+        for (int y = ya + threadIdx.y; y < yb; y += NTY)
+            for (int x = xa + threadIdx.x; x < xb; x += NTX) {
+                const int cx = clampi(x, s, W - 1 - s), cy = clampi(y, s, H - 1 - s);
+                const float lxx = b0[idx(cx, cy + s)] - b0[idx(cx, cy - s)];
+                float lyy = 0.0f + p.n * b1[idx(cx, cy - s)];
+                lyy = lyy + p.wn * b1[idx(cx, cy)];
+                lyy = lyy + p.n * b1[idx(cx, cy + s)];
+                float lxy = 0.0f + p.n * b2[idx(cx, cy - s)];
+                lxy = lxy + p.wn * b2[idx(cx, cy)];
+                lxy = lxy + p.n * b2[idx(cx, cy + s)];
+                const float det = ((lxx * lyy) - (lxy * lxy)) * p.quat;  // detector_response.rs:52
+                b3[idx(x, y)] = det;
+                if (x >= tx0 && x < tx0 + DT && y >= ty0 && y < ty0 + DT) {
+                    const size_t o = (size_t)y * W + x;
+                    od[o] = det;
+                    if (oLxx != nullptr) {
+                        oLxx[(size_t)img * img_px + o] = lxx;
+                        oLyy[(size_t)img * img_px + o] = lyy;
+                        oLxy[(size_t)img * img_px + o] = lxy;
+                    }
+                }
+            }
+    }
+    __syncthreads();
+    {  // stage 5: threshold + strict 4-neighbour maximum + is_out (scale_space_extrema.rs:36-41, 80-87)
+        unsigned int* m = mask + (size_t)img * mask_img_words;
+        for (int y = ty0 + threadIdx.y; y < ty0 + DT; y += NTY) {
+            const int x = tx0 + threadIdx.x;  // DT == NTX: one warp covers one tile row
+            bool cand = false;
+            if (x >= p.xmin && x <= p.xmax && y >= p.ymin && y <= p.ymax) {
+                const float v = b3[idx(x, y)];
+                cand = v > p.thr && v > b3[idx(x + 1, y)] && v > b3[idx(x - 1, y)] && v > b3[idx(x, y - 1)] &&
+                       v > b3[idx(x, y + 1)];
+            }
+            const unsigned int bal = __ballot_sync(0xffffffffu, cand);
+            if (bal != 0 && threadIdx.x == 0) {
+                const int w0 = tx0 >> 5, sh = tx0 & 31;
+                atomicOr(&m[(size_t)y * p.wpr + w0], bal << sh);
+                if (sh != 0 && (bal >> (32 - sh)) != 0) atomicOr(&m[(size_t)y * p.wpr + w0 + 1], bal >> (32 - sh));
+            }
+        }
+    }
+}
+
+// ---- bitmask -> ordered list ------------------------------------------------------------------
+// rows are enumerated level-major; one warp per row
+__device__ __forceinline__ int find_level(const PlanDev* plan, int grow, int* row_in_level) {
+    int l = 0, base = 0;
+    while (l < plan->n_levels - 1 && grow >= base + plan->lv[l].h) {
+        base += plan->lv[l].h;
+        l++;
+    }
+    *row_in_level = grow - base;
+    return l;
+}
+
+__global__ void k_rowcount(const unsigned int* __restrict__ mask, const PlanDev* __restrict__ plan,
+                           unsigned int* __restrict__ rowcount, int total_rows) {
+    const int lane = threadIdx.x & 31;
+    const int grow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int img = blockIdx.y;
+    if (grow >= total_rows) return;
+    int y;
+    const int l = find_level(plan, grow, &y);
+    const LevelDev& lv = plan->lv[l];
+    unsigned int cnt = 0;
+    if (y >= lv.ymin && y <= lv.ymax) {
+        const unsigned int* m = mask + (size_t)img * plan->mask_words + lv.mask_off + (size_t)y * lv.wpr;
+        for (int w = lane; w < lv.wpr; w += 32) cnt += __popc(m[w]);
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0) rowcount[(size_t)img * total_rows + grow] = cnt;
+}
+
+// one block per image: exclusive scan of the row counts, per-level offsets, total
+__global__ void __launch_bounds__(1024)
+k_rowscan(unsigned int* __restrict__ rowcount, const PlanDev* __restrict__ plan, unsigned int* __restrict__ level_off,
+          unsigned int* __restrict__ n_total, unsigned int* __restrict__ err_flags, int total_rows, unsigned int cand_cap) {
+    __shared__ unsigned int warp_sums[32];
+    __shared__ unsigned int carry;
+    const int img = blockIdx.x;
+    unsigned int* rc = rowcount + (size_t)img * total_rows;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < total_rows; base += 1024) {
+        const int i = base + tid;
+        const unsigned int v = (i < total_rows) ? rc[i] : 0;
+        unsigned int incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned int ws = warp_sums[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += t;
+            }
+            warp_sums[lane] = ws;  // inclusive
+        }
+        __syncthreads();
+        const unsigned int woff = wid ? warp_sums[wid - 1] : 0;
+        const unsigned int excl = carry + woff + incl - v;
+        if (i < total_rows) rc[i] = excl;
+        __syncthreads();
+        if (tid == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        // per-level offsets from the scanned rows
+        int row = 0;
+        for (int l = 0; l < plan->n_levels; l++) {
+            level_off[(size_t)img * (kMaxLevels + 1) + l] = (row < total_rows) ? rc[row] : carry;
+            row += plan->lv[l].h;
+        }
+        for (int l = plan->n_levels; l <= kMaxLevels; l++) level_off[(size_t)img * (kMaxLevels + 1) + l] = carry;
+        n_total[img] = carry;
+        if (carry > cand_cap) atomicOr(&err_flags[img], (unsigned int)kErrCandOverflow);
+    }
+}
+
+__global__ void k_scatter(const unsigned int* __restrict__ mask, const PlanDev* __restrict__ plan,
+                          const unsigned int* __restrict__ rowoff, unsigned int* __restrict__ cand, int total_rows,
+                          unsigned int cand_cap) {
+    const int lane = threadIdx.x & 31;
+    const int grow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int img = blockIdx.y;
+    if (grow >= total_rows) return;
+    int y;
+    const int l = find_level(plan, grow, &y);
+    const LevelDev& lv = plan->lv[l];
+    if (y < lv.ymin || y > lv.ymax) return;
+    const unsigned int* m = mask + (size_t)img * plan->mask_words + lv.mask_off + (size_t)y * lv.wpr;
+    unsigned int pos = rowoff[(size_t)img * total_rows + grow];
+    unsigned int* out = cand + (size_t)img * cand_cap;
+    for (int wb = 0; wb < lv.wpr; wb += 32) {
+        const int w = wb + lane;
+        unsigned int bits = (w < lv.wpr) ? m[w] : 0u;
+        const unsigned int c = __popc(bits);
+        unsigned int incl = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        unsigned int at = pos + incl - c;
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1;
+            if (at < cand_cap) out[at] = (unsigned int)(y * lv.w + w * 32 + b);
+            at++;
+        }
+        pos += __shfl_sync(0xffffffffu, incl, 31);
+    }
+}
+
+}  // namespace
+
+// opt in to > 48 KB dynamic shared memory (call once per device, after cudaSetDevice)
+cudaError_t init_detector_attributes() {
+    const int pw = DT + 2 * (2 * kMaxDetScale + 1);
+    return cudaFuncSetAttribute(k_detector, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * pw * pw * (int)sizeof(float));
+}
+
+int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level) {
+    const LevelDev& lv = P.dev.lv[level];
+    DetParams p;
+    p.W = lv.w;
+    p.H = lv.h;
+    p.s = lv.s_det;
+    p.n = P.sch_n[lv.s_det];
+    p.wn = P.sch_wn[lv.s_det];
+    const uint32_t s = (uint32_t)lv.s_det;
+    p.quat = (float)(s * s * s * s);
+    p.thr = P.dev.det_threshold;
+    p.xmin = lv.xmin;
+    p.xmax = lv.xmax;
+    p.ymin = lv.ymin;
+    p.ymax = lv.ymax;
+    p.wpr = lv.wpr;
+    const int HL = 2 * lv.s_det + 1, PW = DT + 2 * HL;
+    const size_t smem = (size_t)5 * PW * PW * sizeof(float);
+    const size_t img_px = (size_t)lv.w * lv.h;
+    const size_t off = (size_t)lv.off * L.batch;
+    // level 0: Lsmooth is Lt (lib.rs:58)
+    const float* ls = (level == 0) ? B.Lt : (B.keep ? B.Lsmooth + off : B.Lsmooth);
+    dim3 grid((lv.w + DT - 1) / DT, (lv.h + DT - 1) / DT, L.batch);
+    k_detector<<<grid, dim3(NTX, NTY), smem, L.stream>>>(
+        ls, img_px, B.Lx + off, B.Ly + off, B.Ldet + off, B.keep ? B.Lxx + off : nullptr, B.keep ? B.Lyy + off : nullptr,
+        B.keep ? B.Lxy + off : nullptr, B.mask + lv.mask_off, (size_t)P.dev.mask_words, p);
+    return 1;
+}
+
+int launch_compact(const Launch& L, const Plan& P, const Buffers& B) {
+    int total_rows = 0;
+    for (int l = 0; l < P.dev.n_levels; l++) total_rows += P.dev.lv[l].h;
+    unsigned int* rowcount = B.rowcount;  // [B][total_rows]
+    const int wpb = 8;
+    dim3 grid((total_rows + wpb - 1) / wpb, L.batch);
+    k_rowcount<<<grid, wpb * 32, 0, L.stream>>>(B.mask, B.plan_dev, rowcount, total_rows);
+    k_rowscan<<<L.batch, 1024, 0, L.stream>>>(rowcount, B.plan_dev, B.cand_level_count, B.n_cand_total, B.err_flags,
+                                              total_rows, L.cand_cap);
+    k_scatter<<<grid, wpb * 32, 0, L.stream>>>(B.mask, B.plan_dev, rowcount, B.cand, total_rows, L.cand_cap);
+    return 3;
+}
+
+}  // namespace akz

@@ -1,0 +1,473 @@
+// keypoints.cu -- cross-scale suppression, "sub-pixel" refinement, dominant orientation, MLDB descriptor.
+//
+// Replaces (reference paths relative to the akaze-rust repository):
+//   find_scale_space_extrema, cache pass + upper-scale filter  akaze/src/ops/scale_space_extrema.rs:43-132
+//   do_subpixel_refinement                                      akaze/src/ops/scale_space_extrema.rs:141-189
+//   compute_main_orientation                                    akaze/src/ops/scale_space_extrema.rs:274-329
+//   extract_descriptors .. mldb_binary_comparisons              akaze/src/ops/descriptors.rs:14-175
+//
+// The cache pass of the reference is a greedy, insertion-order dependent scan: for each
+// candidate, in level-major raster order, the FIRST cache slot holding a keypoint of the same or the
+// previous class_id within `size` pixels decides (replace-in-slot if the candidate is stronger, else
+// drop). That semantics is kept exactly: one warp walks one image's ordered candidate list; the linear
+// cache scan is replaced by a spatial hash (two grids, one per class parity, since only classes L and
+// L-1 can match) whose cells are searched in parallel by the lanes for the LOWEST matching slot.
+#include "common.cuh"
+
+namespace akz {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// K5a: greedy cache pass, one warp per image
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32)
+k_dedup(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ cand, const unsigned int* __restrict__ level_off,
+        const float* __restrict__ ldet_plane, int batch, unsigned int cand_cap, unsigned int kp_cap,
+        volatile float* c_x, volatile float* c_y, volatile float* c_resp, volatile int* c_cls, volatile int* c_next,
+        volatile int* grid, unsigned int* __restrict__ n_cache, unsigned int* __restrict__ err_flags) {
+    const int img = blockIdx.x;
+    const int lane = threadIdx.x;
+    const unsigned int FULL = 0xffffffffu;
+    const int gw = plan->grid_w, gh = plan->grid_h, gshift = plan->grid_shift;
+    const int gcells = gw * gh;
+    c_x += (size_t)img * kp_cap;
+    c_y += (size_t)img * kp_cap;
+    c_resp += (size_t)img * kp_cap;
+    c_cls += (size_t)img * kp_cap;
+    c_next += (size_t)img * kp_cap;
+    grid += (size_t)img * 2 * gcells;
+    const unsigned int* cl = cand + (size_t)img * cand_cap;
+    const unsigned int* lo = level_off + (size_t)img * (kMaxLevels + 1);
+    if (err_flags[img] & kErrCandOverflow) {
+        if (lane == 0) n_cache[img] = 0;
+        return;
+    }
+    unsigned int n = 0;  // cache length (uniform across lanes)
+    bool overflow = false;
+
+    for (int L = 0; L < plan->n_levels && !overflow; L++) {
+        const LevelDev& lv = plan->lv[L];
+        volatile int* g_cur = grid + (size_t)(L & 1) * gcells;   // entries of class L
+        volatile int* g_prev = grid + (size_t)((L + 1) & 1) * gcells;  // entries of class L-1
+        for (int i = lane; i < gcells; i += 32) g_cur[i] = -1;  // drops class L-2
+        __syncwarp();
+        const float ratio = lv.ratio, size = lv.kp_size, size_sq = lv.size_sq, hr = lv.half_ratio_m1;
+        const float* ldet = ldet_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
+        const unsigned int beg = lo[L], end = lo[L + 1];
+        for (unsigned int base = beg; base < end && !overflow; base += 32) {
+            // prefetch up to 32 candidates
+            unsigned int my_flat = 0;
+            float my_resp = 0.0f;
+            if (base + lane < end) {
+                my_flat = cl[base + lane];
+                my_resp = fabsf(ldet[my_flat]);  // scale_space_extrema.rs:44
+            }
+            const int cnt = min(32u, end - base);
+            for (int k = 0; k < cnt; k++) {
+                const unsigned int flat = __shfl_sync(FULL, my_flat, k);
+                const float resp = __shfl_sync(FULL, my_resp, k);
+                const int px = (int)(flat % (unsigned int)lv.w), py = (int)(flat / (unsigned int)lv.w);
+                // :62-65 compares keypoint.point * ratio (level coords scaled) with the cached full-res point
+                const float qx = (float)px * ratio, qy = (float)py * ratio;
+                const int cx0 = max(0, ((int)floorf(qx - size) - 1) >> gshift);
+                const int cx1 = min(gw - 1, ((int)floorf(qx + size) + 1) >> gshift);
+                const int cy0 = max(0, ((int)floorf(qy - size) - 1) >> gshift);
+                const int cy1 = min(gh - 1, ((int)floorf(qy + size) + 1) >> gshift);
+                const int nx = cx1 - cx0 + 1, ny = cy1 - cy0 + 1;
+                const int ncell = nx * ny;
+                const int ntot = (L > 0) ? 2 * ncell : ncell;
+                unsigned int best = 0xffffffffu;
+                for (int c = lane; c < ntot; c += 32) {
+                    const int which = c >= ncell;
+                    const int cc = which ? c - ncell : c;
+                    const int cell = (cy0 + cc / nx) * gw + (cx0 + cc % nx);
+                    int e = which ? g_prev[cell] : g_cur[cell];
+                    while (e >= 0) {
+                        const int ecls = c_cls[e];
+                        if (ecls == L || ecls + 1 == L) {
+                            const float dx = qx - c_x[e], dy = qy - c_y[e];
+                            const float dist = dx * dx + dy * dy;
+                            if (dist <= size_sq && (unsigned int)e < best) best = (unsigned int)e;
+                        }
+                        e = c_next[e];
+                    }
+                }
+                best = __reduce_min_sync(FULL, best);
+                bool do_write = false;
+                unsigned int slot = 0;
+                if (best == 0xffffffffu) {
+                    slot = n;
+                    if (slot >= kp_cap) {
+                        overflow = true;
+                        break;
+                    }
+                    n++;
+                    do_write = true;
+                } else if (resp > c_resp[best]) {  // :67
+                    slot = best;
+                    do_write = true;
+                    if (lane == 0) {
+                        // unlink `best` from the list it is on (class and position of the old occupant)
+                        const int ocls = c_cls[best];
+                        volatile int* g_old = grid + (size_t)(ocls & 1) * gcells;
+                        const int ocx = min(gw - 1, max(0, (int)c_x[best] >> gshift));
+                        const int ocy = min(gh - 1, max(0, (int)c_y[best] >> gshift));
+                        const int ocell = ocy * gw + ocx;
+                        int e = g_old[ocell];
+                        if (e == (int)best) {
+                            g_old[ocell] = c_next[best];
+                        } else {
+                            while (e >= 0) {
+                                const int nxt = c_next[e];
+                                if (nxt == (int)best) {
+                                    c_next[e] = c_next[best];
+                                    break;
+                                }
+                                e = nxt;
+                            }
+                        }
+                    }
+                }
+                if (do_write && lane == 0) {
+                    // :89-92 full-resolution point
+                    const float fx = (float)px * ratio + hr, fy = (float)py * ratio + hr;
+                    c_x[slot] = fx;
+                    c_y[slot] = fy;
+                    c_resp[slot] = resp;
+                    c_cls[slot] = L;
+                    const int ncx = min(gw - 1, max(0, (int)fx >> gshift));
+                    const int ncy = min(gh - 1, max(0, (int)fy >> gshift));
+                    const int ncl = ncy * gw + ncx;
+                    c_next[slot] = g_cur[ncl];
+                    g_cur[ncl] = (int)slot;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    if (lane == 0) {
+        n_cache[img] = n;
+        if (overflow) atomicOr(&err_flags[img], (unsigned int)kErrKpOverflow);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5b: upper-scale filter (:111-129) + pseudo sub-pixel offset (:141-178). One warp per cache slot.
+// keep_flag[i] = 1 iff the slot survives; refined point written back into c_x/c_y.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_filter_refine(const PlanDev* __restrict__ plan, const float* __restrict__ ldet_plane, int batch,
+                                unsigned int kp_cap, const float* __restrict__ c_x, const float* __restrict__ c_y,
+                                const int* __restrict__ c_cls, const unsigned int* __restrict__ n_cache,
+                                float* __restrict__ r_x, float* __restrict__ r_y, unsigned int* __restrict__ keep_flag) {
+    const int img = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const unsigned int n = n_cache[img];
+    const size_t o = (size_t)img * kp_cap;
+    const int warps = (blockDim.x >> 5) * gridDim.x;
+    for (unsigned int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
+        const int cls = c_cls[o + i];
+        const LevelDev& lv = plan->lv[cls];
+        const float xi = c_x[o + i], yi = c_y[o + i];
+        const float size_sq = lv.size_sq;
+        bool rep = false;
+        for (unsigned int j0 = i; j0 < n && !rep; j0 += 32) {
+            const unsigned int j = j0 + lane;
+            bool hit = false;
+            if (j < n && c_cls[o + j] == cls + 1) {
+                const float dx = xi - c_x[o + j], dy = yi - c_y[o + j];
+                const float dist = dx * dx + dy * dy;
+                hit = dist <= size_sq;
+            }
+            rep = __any_sync(0xffffffffu, hit);
+        }
+        if (lane == 0) {
+            bool keep = !rep;
+            const float ratio = lv.ratio;
+            // :147-149 (the division is exact: ratio is a power of two)
+            const int x = (int)roundf(xi / ratio), y = (int)roundf(yi / ratio);
+            const float* D = ldet_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
+            const float x_p = D[(size_t)y * lv.w + x + 1], x_m = D[(size_t)y * lv.w + x - 1];
+            const float y_p = D[(size_t)(y + 1) * lv.w + x], y_m = D[(size_t)(y - 1) * lv.w + x];
+            const float d_x = 0.5f * (x_p - x_m), d_y = 0.5f * (y_p - y_m);
+            const float b0 = -d_x, b1 = -d_y;  // lu.solve's result is dropped (:168-169)
+            if (!(fabsf(b0) <= 1.0f && fabsf(b1) <= 1.0f)) keep = false;
+            float nx = (float)x + b0, ny = (float)y + b1;
+            nx = nx * ratio + lv.half_ratio_m1;
+            ny = ny * ratio + lv.half_ratio_m1;
+            r_x[o + i] = nx;
+            r_y[o + i] = ny;
+            keep_flag[o + i] = keep ? 1u : 0u;
+        }
+    }
+}
+
+// one block per image: exclusive scan of keep_flag -> output slot, survivors counted
+__global__ void __launch_bounds__(1024)
+k_keep_scan(unsigned int* __restrict__ keep_flag, const unsigned int* __restrict__ n_cache, unsigned int* __restrict__ n_kp,
+            unsigned int kp_cap) {
+    __shared__ unsigned int warp_sums[32];
+    __shared__ unsigned int carry;
+    const int img = blockIdx.x;
+    const unsigned int n = n_cache[img];
+    unsigned int* kf = keep_flag + (size_t)img * kp_cap;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) carry = 0;
+    __syncthreads();
+    for (unsigned int base = 0; base < n; base += 1024) {
+        const unsigned int i = base + tid;
+        const unsigned int v = (i < n) ? kf[i] : 0;
+        unsigned int incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) warp_sums[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            unsigned int ws = warp_sums[lane];
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int t = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += t;
+            }
+            warp_sums[lane] = ws;
+        }
+        __syncthreads();
+        const unsigned int excl = carry + (wid ? warp_sums[wid - 1] : 0) + incl - v;
+        // encode: bit 31 = keep, low bits = output position
+        if (i < n) kf[i] = (v ? 0x80000000u : 0u) | excl;
+        __syncthreads();
+        if (tid == 1023) carry = excl + v;
+        __syncthreads();
+    }
+    if (tid == 0) n_kp[img] = carry;
+}
+
+// GAUSS25 of the reference (scale_space_extrema.rs:207-271; numeric table = data)
+__constant__ float c_gauss25[7][7] = {
+    {0.02546481f, 0.02350698f, 0.01849125f, 0.01239505f, 0.00708017f, 0.00344629f, 0.00142946f},
+    {0.02350698f, 0.02169968f, 0.01706957f, 0.01144208f, 0.00653582f, 0.00318132f, 0.00131956f},
+    {0.01849125f, 0.01706957f, 0.01342740f, 0.00900066f, 0.00514126f, 0.00250252f, 0.00103800f},
+    {0.01239505f, 0.01144208f, 0.00900066f, 0.00603332f, 0.00344629f, 0.00167749f, 0.00069579f},
+    {0.00708017f, 0.00653582f, 0.00514126f, 0.00344629f, 0.00196855f, 0.00095820f, 0.00039744f},
+    {0.00344629f, 0.00318132f, 0.00250252f, 0.00167749f, 0.00095820f, 0.00046640f, 0.00019346f},
+    {0.00142946f, 0.00131956f, 0.00103800f, 0.00069579f, 0.00039744f, 0.00019346f, 0.00008024f},
+};
+
+// ------------------------------------------------------------------------------------------------
+// K5c: dominant orientation, one thread per surviving keypoint (:274-329).
+// angs[k] = atan2(res_y,res_y) is pi/4 for res_y>0 and <= 0 otherwise, so a sample is inside a window
+// iff res_y>0 and the window contains pi/4; which of the 42 windows do is decided once on the host
+// with the reference's own f32 arithmetic (plan.orient_window_mask). sum_x/sum_y are never reset
+// between windows (:301-302), so the samples are re-accumulated, in sample order, once per such window.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_orientation(const PlanDev* __restrict__ plan, const float* __restrict__ lx_plane, const float* __restrict__ ly_plane,
+              int batch, unsigned int kp_cap, const float* __restrict__ r_x, const float* __restrict__ r_y,
+              const float* __restrict__ c_resp, const int* __restrict__ c_cls, const unsigned int* __restrict__ keep_flag,
+              const unsigned int* __restrict__ n_cache, akz_keypoint* __restrict__ kps, unsigned int* __restrict__ err_flags) {
+    const int img = blockIdx.y;
+    const unsigned int n = n_cache[img];
+    const size_t o = (size_t)img * kp_cap;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned int kf = keep_flag[o + i];
+        if (!(kf & 0x80000000u)) continue;
+        const unsigned int pos = kf & 0x7fffffffu;
+        const int cls = c_cls[o + i];
+        const LevelDev& lv = plan->lv[cls];
+        const float ratio = lv.ratio, s = lv.s_smp;
+        const float ptx = r_x[o + i], pty = r_y[o + i];
+        const float xf = ptx / ratio, yf = pty / ratio;
+        const float* Lx = lx_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
+        const float* Ly = ly_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
+        float rx[109], ry[109];
+        int idx = 0;
+        bool oob = false;
+        for (int a = -6; a <= 6; a++)
+            for (int b = -6; b <= 6; b++)
+                if (a * a + b * b < 36) {
+                    int iy = (int)roundf(yf + (float)b * s);
+                    int ix = (int)roundf(xf + (float)a * s);
+                    if (ix < 0 || iy < 0 || ix >= lv.w || iy >= lv.h) {
+                        oob = true;
+                        ix = min(max(ix, 0), lv.w - 1);
+                        iy = min(max(iy, 0), lv.h - 1);
+                    }
+                    const int ia = a < 0 ? -a : a, ib = b < 0 ? -b : b;
+                    const float gw = c_gauss25[ia][ib];
+                    rx[idx] = gw * Lx[(size_t)iy * lv.w + ix];
+                    ry[idx] = gw * Ly[(size_t)iy * lv.w + ix];
+                    idx++;
+                }
+        float sum_x = 0.0f, sum_y = 0.0f, maxv = 0.0f, angle = 0.0f;
+        unsigned long long wm = plan->orient_window_mask;
+        for (int w = 0; w < plan->n_orient_windows; w++, wm >>= 1) {
+            if (wm & 1ull) {
+                for (int k = 0; k < 109; k++)
+                    if (ry[k] > 0.0f) {
+                        sum_x = sum_x + rx[k];
+                        sum_y = sum_y + ry[k];
+                    }
+            }
+            const float val = sum_x * sum_x + sum_y * sum_y;
+            if (val > maxv) {
+                maxv = val;
+                // f32::atan2 -> libm atan2f; evaluated in f64 and rounded once (correctly rounded
+                // except for vanishingly rare double-rounding cases)
+                angle = (float)atan2((double)sum_y, (double)sum_x);
+            }
+        }
+        akz_keypoint kp;
+        kp.x = ptx;
+        kp.y = pty;
+        kp.response = c_resp[o + i];
+        kp.size = lv.kp_size;
+        kp.octave = (uint32_t)lv.octave;
+        kp.class_id = (uint32_t)cls;
+        kp.angle = angle;
+        kps[o + pos] = kp;
+        if (oob) atomicOr(&err_flags[img], (unsigned int)kErrBounds);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: MLDB descriptor, one warp per keypoint (descriptors.rs:37-175). Lanes 0..28 own the 4+9+16
+// grid cells and accumulate their samples sequentially (k outer, l inner) exactly like the reference;
+// comparisons are packed LSB-first: grid level, then channel, then pairs i<j.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plane, const float* __restrict__ lx_plane,
+             const float* __restrict__ ly_plane, int batch, unsigned int kp_cap, const akz_keypoint* __restrict__ kps,
+             const unsigned int* __restrict__ n_kp, uint8_t* __restrict__ desc, unsigned int* __restrict__ err_flags) {
+    __shared__ float s_val[8][29 * 3];
+    __shared__ unsigned int s_bits[8][16];
+    const int img = blockIdx.y;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const unsigned int n = min(n_kp[img], kp_cap);
+    const int warps = (blockDim.x >> 5) * gridDim.x;
+    const int nch = plan->channels;
+    const int pattern = plan->pattern_size;
+    // sample_size per grid level: ceil(pattern * {1, 2/3, 1/2}) in f32 (descriptors.rs:50,61)
+    const float pf = (float)pattern;
+    const int step0 = (int)ceilf(pf * 1.0f), step1 = (int)ceilf(pf * (2.0f / 3.0f)), step2 = (int)ceilf(pf * (1.0f / 2.0f));
+    // cells per axis actually produced by the step_by loops (descriptors.rs:102-103)
+    const int n0 = (2 * pattern + step0 - 1) / step0, n1 = (2 * pattern + step1 - 1) / step1, n2 = (2 * pattern + step2 - 1) / step2;
+    for (unsigned int kidx = blockIdx.x * (blockDim.x >> 5) + wib; kidx < n; kidx += warps) {
+        const akz_keypoint kp = kps[(size_t)img * kp_cap + kidx];
+        const LevelDev& lv = plan->lv[kp.class_id];
+        const float ratio = lv.ratio;
+        const float scale = lv.s_smp;
+        const float xf = kp.x / ratio, yf = kp.y / ratio;
+        const float co = (float)cos((double)kp.angle), si = (float)sin((double)kp.angle);
+        const float* Lt = lt_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
+        const float* Lx = lx_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
+        const float* Ly = ly_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
+        // which cell does this lane own?
+        int glevel = -1, ci = 0, cj = 0, step = 0, cell_in_level = 0;
+        if (lane < n0 * n0) {
+            glevel = 0; step = step0; cell_in_level = lane; ci = lane / n0; cj = lane % n0;
+        } else if (lane < n0 * n0 + n1 * n1) {
+            glevel = 1; step = step1; cell_in_level = lane - n0 * n0; ci = cell_in_level / n1; cj = cell_in_level % n1;
+        } else if (lane < n0 * n0 + n1 * n1 + n2 * n2) {
+            glevel = 2; step = step2; cell_in_level = lane - n0 * n0 - n1 * n1; ci = cell_in_level / n2; cj = cell_in_level % n2;
+        }
+        bool oob = false;
+        if (glevel >= 0) {
+            const int i0 = -pattern + ci * step, j0 = -pattern + cj * step;
+            float di = 0.0f, dx = 0.0f, dy = 0.0f;
+            int nsamples = 0;
+            for (int k = i0; k < i0 + step; k++)
+                for (int l = j0; l < j0 + step; l++) {
+                    const float lf = (float)l + 0.5f, kf = (float)k + 0.5f;
+                    const float sample_y = yf + (lf * co * scale + kf * si * scale);
+                    const float sample_x = xf + (-lf * si * scale + kf * co * scale);
+                    int y1 = (int)roundf(sample_y), x1 = (int)roundf(sample_x);
+                    if (x1 < 0 || y1 < 0 || x1 >= lv.w || y1 >= lv.h) {
+                        oob = true;
+                        x1 = min(max(x1, 0), lv.w - 1);
+                        y1 = min(max(y1, 0), lv.h - 1);
+                    }
+                    const size_t at = (size_t)y1 * lv.w + x1;
+                    di = di + Lt[at];
+                    if (nch > 1) {
+                        const float rx = Lx[at], ry = Ly[at];
+                        if (nch == 2) {
+                            dx = dx + sqrtf(rx * rx + ry * ry);
+                        } else {
+                            const float rry = rx * co + ry * si;
+                            const float rrx = -rx * si + ry * co;
+                            dx = dx + rrx;
+                            dy = dy + rry;
+                        }
+                    }
+                    nsamples++;
+                }
+            const float ns = (float)nsamples;
+            s_val[wib][lane * 3 + 0] = di / ns;
+            s_val[wib][lane * 3 + 1] = dx / ns;
+            s_val[wib][lane * 3 + 2] = dy / ns;
+        }
+        if (lane < 16) s_bits[wib][lane] = 0;
+        __syncwarp();
+        // comparisons: bit position = dpos (descriptors.rs:161-173)
+        int dpos_base = 0, cell_base = 0;
+        for (int g = 0; g < 3; g++) {
+            const int cnt = (g == 0 ? n0 * n0 : (g == 1 ? n1 * n1 : n2 * n2));
+            const int pairs = cnt * (cnt - 1) / 2;
+            for (int pos = 0; pos < nch; pos++) {
+                for (int pidx = lane; pidx < pairs; pidx += 32) {
+                    // unrank pidx -> (i,j), i<j, row-major over i
+                    int i = 0, rem = pidx;
+                    while (rem >= cnt - 1 - i) {
+                        rem -= cnt - 1 - i;
+                        i++;
+                    }
+                    const int j = i + 1 + rem;
+                    const float vi = s_val[wib][(cell_base + i) * 3 + pos];
+                    const float vj = s_val[wib][(cell_base + j) * 3 + pos];
+                    if (vi > vj) {
+                        const int dpos = dpos_base + pos * pairs + pidx;
+                        atomicOr(&s_bits[wib][dpos >> 5], 1u << (dpos & 31));
+                    }
+                }
+            }
+            dpos_base += nch * pairs;
+            cell_base += cnt;
+        }
+        __syncwarp();
+        if (lane < 16) {
+            unsigned int* out = (unsigned int*)(desc + ((size_t)img * kp_cap + kidx) * kDescStride);
+            out[lane] = s_bits[wib][lane];
+        }
+        if (oob && glevel >= 0) atomicOr(&err_flags[img], (unsigned int)kErrBounds);
+        __syncwarp();
+    }
+}
+
+}  // namespace
+
+int launch_dedup(const Launch& L, const Plan& P, const Buffers& B) {
+    k_dedup<<<L.batch, 32, 0, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap, L.kp_cap,
+                                           B.c_x, B.c_y, B.c_resp, B.c_cls, B.c_next, B.grid, B.n_cache, B.err_flags);
+    return 1;
+}
+
+int launch_finalize(const Launch& L, const Plan& P, const Buffers& B) {
+    float* r_x = B.r_x;
+    float* r_y = B.r_y;
+    dim3 g1(64, L.batch);
+    k_filter_refine<<<g1, 256, 0, L.stream>>>(B.plan_dev, B.Ldet, L.batch, L.kp_cap, B.c_x, B.c_y, B.c_cls, B.n_cache, r_x,
+                                              r_y, B.keep_flag);
+    k_keep_scan<<<L.batch, 1024, 0, L.stream>>>(B.keep_flag, B.n_cache, B.n_kp, L.kp_cap);
+    dim3 g3(16, L.batch);
+    k_orientation<<<g3, 128, 0, L.stream>>>(B.plan_dev, B.Lx, B.Ly, L.batch, L.kp_cap, r_x, r_y, B.c_resp, B.c_cls, B.keep_flag,
+                                            B.n_cache, B.kps, B.err_flags);
+    return 3;
+}
+
+int launch_descriptors(const Launch& L, const Plan& P, const Buffers& B) {
+    dim3 g(32, L.batch);
+    k_descriptor<<<g, 256, 0, L.stream>>>(B.plan_dev, B.Lt, B.Lx, B.Ly, L.batch, L.kp_cap, B.kps, B.n_kp, B.desc, B.err_flags);
+    return 1;
+}
+
+}  // namespace akz

@@ -1,0 +1,180 @@
+/*
+ * akaze_b200.h -- C ABI of the B200-native A-KAZE engine (libakaze_b200.so, CUDA sm_100a).
+ *
+ * Drop-in boundary for the hot path of indianajohn/akaze-rust. The reference has no FFI seam of its
+ * own; the boundary is its public Rust API, and these entry points are what a thin Rust `ffi.rs`
+ * binds. Each entry point cites the reference interface it replaces
+ * (paths relative to the reference repository).
+ *
+ * Conventions: every function returns an int status (AKZ_OK == 0); akz_last_error() gives a
+ * thread-local message for the last failure on the calling thread. Inputs are caller-owned plain
+ * buffers; outputs are either caller-provided buffers or library-owned handles released with the
+ * matching akz_*_free. A context is bound to one CUDA device and is safe to use from one thread
+ * at a time. There is NO CPU fallback: every entry point that computes fails with AKZ_ERR_CUDA if
+ * no usable sm_100 device is present.
+ */
+#ifndef AKAZE_B200_H
+#define AKAZE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AKZ_DESCRIPTOR_STRIDE 64 /* bytes per descriptor row in every dense descriptor array (61 used) */
+
+enum akz_status {
+    AKZ_OK = 0,
+    AKZ_ERR_INVALID = 1,  /* bad argument */
+    AKZ_ERR_CUDA = 2,     /* CUDA runtime / driver error, or no device */
+    AKZ_ERR_CAPACITY = 3, /* image, batch, candidate or keypoint count exceeds the context's limits */
+    AKZ_ERR_BOUNDS = 4,   /* input on which the reference would panic (out-of-image sample) */
+    AKZ_ERR_NOMEM = 5
+};
+
+/* types::evolution::Config, field for field (akaze/src/types/evolution.rs:8-38; defaults :41-54). */
+typedef struct akz_config {
+    uint32_t num_sublevels;
+    uint32_t max_octave_evolution;
+    double base_scale_offset;
+    double initial_contrast; /* never read by the reference either */
+    double contrast_percentile;
+    uint64_t contrast_factor_num_bins;
+    double derivative_factor;
+    double detector_threshold;
+    uint64_t descriptor_channels;
+    uint64_t descriptor_pattern_size;
+} akz_config;
+
+/* types::keypoint::Keypoint (akaze/src/types/keypoint.rs:8-30); usize fields narrowed to u32. */
+typedef struct akz_keypoint {
+    float x, y; /* point.0, point.1 */
+    float response;
+    float size;
+    uint32_t octave;
+    uint32_t class_id;
+    float angle;
+} akz_keypoint;
+
+/* types::feature_match::Match (akaze/src/types/feature_match.rs:9-16). */
+typedef struct akz_match {
+    uint64_t index_0;
+    uint64_t index_1;
+    double distance;
+} akz_match;
+
+/* Per-level metadata of types::evolution::EvolutionStep (akaze/src/types/evolution.rs:59-92). */
+typedef struct akz_level_info {
+    uint32_t octave, sublevel, sigma_size;
+    uint32_t width, height;
+    uint32_t n_steps; /* fed_tau_steps.len() */
+    double esigma, etime;
+} akz_level_info;
+
+/* The ten images of an EvolutionStep (evolution.rs:70-89). */
+enum akz_image_kind {
+    AKZ_LT = 0, AKZ_LSMOOTH = 1, AKZ_LX = 2, AKZ_LY = 3, AKZ_LXX = 4, AKZ_LYY = 5, AKZ_LXY = 6,
+    AKZ_LFLOW = 7, AKZ_LSTEP = 8, AKZ_LDET = 9
+};
+
+/* Per-query result of the brute-force matcher before the Lowe test (feature_matching.rs:37-50):
+ * the two smallest Hamming distances of {d_j} U {10000,10000} and the lowest j attaining the minimum. */
+typedef struct akz_top2 {
+    uint32_t best_idx;
+    uint16_t best;
+    uint16_t second;
+} akz_top2;
+
+/* akz_create flags */
+#define AKZ_KEEP_EVOLUTIONS 1u /* retain all ten images of every level so that
+                                  akz_features_evolution_download works (debug / full drop-in of the
+                                  Vec<EvolutionStep> return value; costs memory and bandwidth) */
+
+typedef struct akz_context akz_context;
+typedef struct akz_features akz_features;
+
+/* ---- housekeeping --------------------------------------------------------------------------- */
+const char *akz_last_error(void);
+const char *akz_version(void);
+/* Config::default() (evolution.rs:41-54) */
+int akz_default_config(akz_config *cfg);
+/* Creates an engine on `device` able to extract from images up to max_width x max_height, up to
+ * max_batch images per call. Fails with AKZ_ERR_CUDA when there is no sm_100 GPU. */
+int akz_create(int device, uint32_t max_width, uint32_t max_height, uint32_t max_batch, uint32_t flags,
+               akz_context **out);
+void akz_destroy(akz_context *ctx);
+/* The CUDA stream (cudaStream_t) all work of this context is issued on; for event timing. */
+void *akz_context_stream(akz_context *ctx);
+/* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
+uint64_t akz_context_launch_count(const akz_context *ctx);
+/* Per-image capacities of the candidate list (4-neighbour maxima inside the descriptor margin) and of
+ * the keypoint cache; exceeding either makes the extraction fail with AKZ_ERR_CAPACITY instead of
+ * truncating. Defaults: 262144 candidates, 65536 keypoints. Call before the first extraction. */
+int akz_context_set_limits(akz_context *ctx, uint32_t max_candidates, uint32_t max_keypoints);
+
+/* ---- extraction: replaces akaze::extract_features (akaze/src/lib.rs:167-194) from the
+ *      GrayFloatImage on; decode + to_luma (lib.rs:171, image.rs:128) stay with the host ------- */
+/* gray: 8-bit luma, row stride in bytes; the u8 -> unit float conversion of
+ * create_unit_float_image (image.rs:127-140) runs on the device. */
+int akz_extract_u8(akz_context *ctx, const uint8_t *gray, uint32_t width, uint32_t height, size_t stride,
+                   const akz_config *cfg, akz_features **out);
+/* unit_gray: exactly the GrayFloatImage buffer of image.rs:127-140 (row-major, width*height). */
+int akz_extract_f32(akz_context *ctx, const float *unit_gray, uint32_t width, uint32_t height,
+                    const akz_config *cfg, akz_features **out);
+/* n images of identical size; outs[n] receives one handle per image. */
+int akz_extract_batch_u8(akz_context *ctx, uint32_t n, const uint8_t *const *grays, uint32_t width,
+                         uint32_t height, size_t stride, const akz_config *cfg, akz_features **outs);
+/* Throughput path: the n images already sit in device memory (n * height * stride bytes, contiguous);
+ * keypoints and descriptors stay on the device and only the per-image counts come back.
+ * counts[n] receives the number of keypoints per image. Device result pointers (valid until the next
+ * extraction on this context) via akz_context_device_results. */
+int akz_extract_batch_u8_device(akz_context *ctx, uint32_t n, const void *d_grays, uint32_t width,
+                                uint32_t height, size_t stride, const akz_config *cfg, uint32_t *counts);
+/* d_keypoints: akz_keypoint[n][kp_capacity]; d_descriptors: uint8_t[n][kp_capacity][64]. */
+int akz_context_device_results(akz_context *ctx, void **d_keypoints, void **d_descriptors,
+                               uint32_t *kp_capacity);
+
+uint64_t akz_features_count(const akz_features *f);
+const akz_keypoint *akz_features_keypoints(const akz_features *f);
+/* count x AKZ_DESCRIPTOR_STRIDE bytes; bytes [descriptor_len, 64) of every row are zero */
+const uint8_t *akz_features_descriptors(const akz_features *f);
+uint32_t akz_features_descriptor_len(const akz_features *f); /* (162*channels+7)/8, descriptors.rs:42-46 */
+uint32_t akz_features_num_levels(const akz_features *f);
+int akz_features_level_info(const akz_features *f, uint32_t level, akz_level_info *out);
+/* fed_tau_steps of a level (evolution.rs:91,153); copies min(cap, n_steps) doubles */
+int akz_features_fed_tau(const akz_features *f, uint32_t level, double *out, uint32_t cap);
+double akz_features_contrast_factor(const akz_features *f); /* contrast_factor.rs:18-71 result */
+/* candidate / cache statistics of find_scale_space_extrema (scale_space_extrema.rs:12-132) */
+uint64_t akz_features_num_candidates(const akz_features *f);
+uint64_t akz_features_num_cache(const akz_features *f);
+/* Copies one image of one EvolutionStep (width*height floats) to dst. Needs AKZ_KEEP_EVOLUTIONS and
+ * must be called before the next extraction on the same context. */
+int akz_features_evolution_download(const akz_features *f, uint32_t level, int kind, float *dst);
+void akz_features_free(akz_features *f);
+
+/* ---- matching: replaces ops::feature_matching::descriptor_match
+ *      (akaze/src/ops/feature_matching.rs:23-94), the first half of akaze::match_features
+ *      (lib.rs:252-266); RANSAC (lib.rs:267) stays with the host --------------------------------- */
+/* Brute-force Hamming top-2. q, db: n x stride bytes, the first desc_len bytes of each row compared
+ * (desc_len <= 64). out[nq]. Host buffers. */
+int akz_match_top2(akz_context *ctx, const uint8_t *q, uint64_t nq, const uint8_t *db, uint64_t ndb,
+                   uint32_t desc_len, size_t stride, akz_top2 *out);
+/* Same on device-resident descriptors padded to 64-byte rows (bytes >= desc_len must be zero);
+ * d_out: akz_top2[nq] in device memory; best_idx is offset by db_index_base (for sharded databases). */
+int akz_match_top2_device(akz_context *ctx, const void *d_q, uint64_t nq, const void *d_db, uint64_t ndb,
+                          uint32_t db_index_base, void *d_out);
+/* Merges per-shard results: d_parts is akz_top2[n_parts][nq] (shards ordered by ascending database
+ * index range); d_out: akz_top2[nq]. Same tie rule as the sequential scan (lowest index wins). */
+int akz_merge_top2_device(akz_context *ctx, const void *d_parts, uint32_t n_parts, uint64_t nq, void *d_out);
+/* descriptor_match proper: top-2 on the device, then the f64 Lowe-ratio and threshold tests
+ * (feature_matching.rs:61-80) on the host. out must hold n0 entries; *n_out receives the count. */
+int akz_descriptor_match(akz_context *ctx, const uint8_t *d0, uint64_t n0, const uint8_t *d1, uint64_t n1,
+                         uint32_t desc_len, size_t stride, uint64_t distance_threshold, double lowes_ratio,
+                         akz_match *out, uint64_t *n_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
