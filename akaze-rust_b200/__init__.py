@@ -26,6 +26,8 @@ AKZ_KEEP_EVOLUTIONS = 1
 IMAGE_KINDS = {"Lt": 0, "Lsmooth": 1, "Lx": 2, "Ly": 3, "Lxx": 4, "Lyy": 5, "Lxy": 6, "Lflow": 7,
                "Lstep": 8, "Ldet": 9}
 
+STAGES = ("level0", "contrast", "prep", "fed", "detector", "compact", "dedup", "finalize", "descriptor")
+
 KEYPOINT_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("response", "<f4"), ("size", "<f4"),
                            ("octave", "<u4"), ("class_id", "<u4"), ("angle", "<f4")])
 TOP2_DTYPE = np.dtype([("best_idx", "<u4"), ("best", "<u2"), ("second", "<u2")])
@@ -75,7 +77,7 @@ _lib = None
 # every symbol include/akaze_b200.h declares
 EXPORTS = [
     "akz_last_error", "akz_version", "akz_default_config", "akz_create", "akz_destroy", "akz_context_stream",
-    "akz_context_launch_count", "akz_context_set_limits", "akz_extract_u8", "akz_extract_f32",
+    "akz_context_launch_count", "akz_context_set_limits", "akz_context_enable_timing", "akz_context_stage_times", "akz_extract_u8", "akz_extract_f32",
     "akz_extract_batch_u8", "akz_extract_batch_u8_device", "akz_context_device_results", "akz_features_count",
     "akz_features_keypoints", "akz_features_descriptors", "akz_features_descriptor_len",
     "akz_features_num_levels", "akz_features_level_info", "akz_features_fed_tau",
@@ -106,6 +108,8 @@ def lib():
     L.akz_context_launch_count.argtypes = [vp]
     L.akz_context_launch_count.restype = C.c_uint64
     L.akz_context_set_limits.argtypes = [vp, C.c_uint32, C.c_uint32]
+    L.akz_context_enable_timing.argtypes = [vp, C.c_int]
+    L.akz_context_stage_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
     L.akz_extract_u8.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_size_t, C.POINTER(Config), C.POINTER(vp)]
     L.akz_extract_f32.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.POINTER(Config), C.POINTER(vp)]
     L.akz_extract_batch_u8.argtypes = [vp, C.c_uint32, C.POINTER(vp), C.c_uint32, C.c_uint32, C.c_size_t,
@@ -269,6 +273,16 @@ class Engine:
     @property
     def launch_count(self):
         return lib().akz_context_launch_count(self._h)
+
+    def enable_timing(self, on=True):
+        _check(lib().akz_context_enable_timing(self._h, int(on)))
+
+    def stage_times(self, reset=False):
+        """{stage: (milliseconds, launches)} accumulated by CUDA events since the last reset."""
+        ms = (C.c_double * len(STAGES))()
+        ln = (C.c_uint64 * len(STAGES))()
+        _check(lib().akz_context_stage_times(self._h, ms, ln, int(reset)))
+        return {name: (ms[i], ln[i]) for i, name in enumerate(STAGES)}
 
     # -- extraction
     def extract_u8(self, gray, config=None):

@@ -279,6 +279,14 @@ struct akz_context {
     int alloc_batch = 0;           // batch the buffers are sized for
     std::vector<void*> allocs;     // everything in buf
     int cur_batch = 0;
+    // per-stage timing
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
+    std::vector<int> ev_stage;       // stage of each used event pair
+    std::vector<int> ev_launches;
+    size_t ev_used = 0;
+    double stage_ms[AKZ_NUM_STAGES] = {0};
+    uint64_t stage_launches[AKZ_NUM_STAGES] = {0};
     // matcher scratch
     void* m_q = nullptr;
     void* m_db = nullptr;
@@ -404,6 +412,44 @@ static int prepare(akz_context* c, uint32_t n, uint32_t w, uint32_t h, const akz
     return ensure_buffers(c, (int)n, changed);
 }
 
+// brackets one stage's launches with events when timing is on
+struct StageTimer {
+    akz_context* c;
+    int stage;
+    size_t slot = (size_t)-1;
+    StageTimer(akz_context* ctx, int st) : c(ctx), stage(st) {
+        if (!c->timing) return;
+        if (c->ev_used == c->ev_pool.size()) {
+            cudaEvent_t a, b;
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            c->ev_pool.push_back({a, b});
+            c->ev_stage.push_back(0);
+            c->ev_launches.push_back(0);
+        }
+        slot = c->ev_used++;
+        c->ev_stage[slot] = stage;
+        cudaEventRecord(c->ev_pool[slot].first, c->stream);
+    }
+    void done(int launches) {
+        if (slot == (size_t)-1) return;
+        c->ev_launches[slot] = launches;
+        cudaEventRecord(c->ev_pool[slot].second, c->stream);
+    }
+};
+
+// folds finished event pairs into the per-stage totals (stream must be idle)
+static void harvest_timing(akz_context* c) {
+    for (size_t i = 0; i < c->ev_used; i++) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, c->ev_pool[i].first, c->ev_pool[i].second) == cudaSuccess) {
+            c->stage_ms[c->ev_stage[i]] += (double)ms;
+            c->stage_launches[c->ev_stage[i]] += (uint64_t)c->ev_launches[i];
+        }
+    }
+    c->ev_used = 0;
+}
+
 // runs the whole pipeline on inputs already in device memory; results stay on the device
 static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8, size_t in_stride) {
     const Plan& P = c->plan;
@@ -413,19 +459,27 @@ static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8
     c->cur_batch = (int)n;
     CK(cudaMemsetAsync(B.mask, 0, (size_t)P.dev.mask_words * n * sizeof(unsigned int), c->stream));
     CK(cudaMemsetAsync(B.err_flags, 0, n * sizeof(unsigned int), c->stream));
-    int k = 0;
-    k += launch_level0(L, P, B, d_in, is_u8, in_stride);
-    k += launch_contrast(L, P, B);
-    k += launch_detector(L, P, B, 0);
-    for (int l = 1; l < P.dev.n_levels; l++) {
-        k += launch_prep(L, P, B, l);
-        k += launch_fed(L, P, B, l);
-        k += launch_detector(L, P, B, l);
+    int k = 0, j;
+#define STAGE(st, expr)          \
+    {                            \
+        StageTimer t__(c, st);   \
+        j = (expr);              \
+        t__.done(j);             \
+        k += j;                  \
     }
-    k += launch_compact(L, P, B);
-    k += launch_dedup(L, P, B);
-    k += launch_finalize(L, P, B);
-    k += launch_descriptors(L, P, B);
+    STAGE(AKZ_STAGE_LEVEL0, launch_level0(L, P, B, d_in, is_u8, in_stride));
+    STAGE(AKZ_STAGE_CONTRAST, launch_contrast(L, P, B));
+    STAGE(AKZ_STAGE_DETECTOR, launch_detector(L, P, B, 0));
+    for (int l = 1; l < P.dev.n_levels; l++) {
+        STAGE(AKZ_STAGE_PREP, launch_prep(L, P, B, l));
+        STAGE(AKZ_STAGE_FED, launch_fed(L, P, B, l));
+        STAGE(AKZ_STAGE_DETECTOR, launch_detector(L, P, B, l));
+    }
+    STAGE(AKZ_STAGE_COMPACT, launch_compact(L, P, B));
+    STAGE(AKZ_STAGE_DEDUP, launch_dedup(L, P, B));
+    STAGE(AKZ_STAGE_FINALIZE, launch_finalize(L, P, B));
+    STAGE(AKZ_STAGE_DESCRIPTOR, launch_descriptors(L, P, B));
+#undef STAGE
     c->launches += (uint64_t)k;
     CK(cudaGetLastError());
     return AKZ_OK;
@@ -449,6 +503,7 @@ static int fetch_stats(akz_context* c, uint32_t n, BatchStats* s) {
     CK(cudaMemcpyAsync(s->err.data(), B.err_flags, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaMemcpyAsync(s->kcontrast.data(), B.kcontrast, (size_t)n * kMaxLevels * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
+    if (c->timing) harvest_timing(c);
     for (uint32_t i = 0; i < n; i++) {
         if (s->err[i] & kErrCandOverflow) return fail(AKZ_ERR_CAPACITY, "candidate list overflow (raise max_candidates)");
         if (s->err[i] & kErrKpOverflow) return fail(AKZ_ERR_CAPACITY, "keypoint cache overflow (raise max_keypoints)");
@@ -542,12 +597,35 @@ void akz_destroy(akz_context* c) {
     cudaFree(c->m_db);
     cudaFree(c->m_parts);
     cudaFree(c->m_out);
+    for (auto& e : c->ev_pool) {
+        cudaEventDestroy(e.first);
+        cudaEventDestroy(e.second);
+    }
     cudaStreamDestroy(c->stream);
     delete c;
 }
 
 void* akz_context_stream(akz_context* c) { return c ? (void*)c->stream : nullptr; }
 uint64_t akz_context_launch_count(const akz_context* c) { return c ? c->launches : 0; }
+
+int akz_context_enable_timing(akz_context* c, int enable) {
+    if (!c) return fail(AKZ_ERR_INVALID, "null context");
+    c->timing = enable != 0;
+    return AKZ_OK;
+}
+
+int akz_context_stage_times(akz_context* c, double* ms, uint64_t* launches, int reset) {
+    if (!c) return fail(AKZ_ERR_INVALID, "null context");
+    for (int i = 0; i < AKZ_NUM_STAGES; i++) {
+        if (ms) ms[i] = c->stage_ms[i];
+        if (launches) launches[i] = c->stage_launches[i];
+        if (reset) {
+            c->stage_ms[i] = 0.0;
+            c->stage_launches[i] = 0;
+        }
+    }
+    return AKZ_OK;
+}
 
 int akz_context_set_limits(akz_context* c, uint32_t max_candidates, uint32_t max_keypoints) {
     if (!c || max_candidates == 0 || max_keypoints == 0) return fail(AKZ_ERR_INVALID, "bad limits");

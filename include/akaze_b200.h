@@ -109,6 +109,15 @@ void akz_destroy(akz_context *ctx);
 void *akz_context_stream(akz_context *ctx);
 /* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
 uint64_t akz_context_launch_count(const akz_context *ctx);
+/* Per-stage device timing: when enabled, every extraction brackets each stage's launches with CUDA events
+ * on the context's stream. akz_context_stage_times copies the accumulated milliseconds and launch counts
+ * (AKZ_NUM_STAGES entries each, order of enum akz_stage) and optionally resets them. */
+enum akz_stage {
+    AKZ_STAGE_LEVEL0 = 0, AKZ_STAGE_CONTRAST = 1, AKZ_STAGE_PREP = 2, AKZ_STAGE_FED = 3, AKZ_STAGE_DETECTOR = 4,
+    AKZ_STAGE_COMPACT = 5, AKZ_STAGE_DEDUP = 6, AKZ_STAGE_FINALIZE = 7, AKZ_STAGE_DESCRIPTOR = 8, AKZ_NUM_STAGES = 9
+};
+int akz_context_enable_timing(akz_context *ctx, int enable);
+int akz_context_stage_times(akz_context *ctx, double *ms, uint64_t *launches, int reset);
 /* Per-image capacities of the candidate list (4-neighbour maxima inside the descriptor margin) and of
  * the keypoint cache; exceeding either makes the extraction fail with AKZ_ERR_CAPACITY instead of
  * truncating. Defaults: 262144 candidates, 65536 keypoints. Call before the first extraction. */
