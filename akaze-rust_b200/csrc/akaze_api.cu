@@ -253,9 +253,9 @@ std::string build_plan(uint32_t w, uint32_t h, const akz_config& cfg, Plan* P) {
         D.orient_window_mask = m;
         D.n_orient_windows = wi;
     }
-    // dedup hash grid: cells of 16 px (32 px for very large images)
+    // dedup hash grid: cells of 16 px, doubled until the grid fits the shared-memory pass (8448 cells)
     D.grid_shift = 4;
-    while ((((int)w >> D.grid_shift) + 1) * (((int)h >> D.grid_shift) + 1) > (1 << 17)) D.grid_shift++;
+    while ((((int)w >> D.grid_shift) + 1) * (((int)h >> D.grid_shift) + 1) > 8448) D.grid_shift++;
     D.grid_w = ((int)w >> D.grid_shift) + 1;
     D.grid_h = ((int)h >> D.grid_shift) + 1;
     return "";
@@ -584,6 +584,7 @@ int akz_create(int device, uint32_t max_width, uint32_t max_height, uint32_t max
     c->flags = flags;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(init_detector_attributes());
+    CK(init_keypoint_attributes());
     *out = c.release();
     return AKZ_OK;
 }

@@ -151,6 +151,7 @@ cudaError_t init_detector_attributes();
 int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level);
 int launch_compact(const Launch& L, const Plan& P, const Buffers& B);
 // keypoints.cu
+cudaError_t init_keypoint_attributes();
 int launch_dedup(const Launch& L, const Plan& P, const Buffers& B);
 int launch_finalize(const Launch& L, const Plan& P, const Buffers& B);
 int launch_descriptors(const Launch& L, const Plan& P, const Buffers& B);

@@ -17,8 +17,11 @@
 namespace akz {
 namespace {
 
+__device__ __forceinline__ bool image_fits_smem_pass(const PlanDev* plan, const unsigned int* lo);
+
 // ------------------------------------------------------------------------------------------------
-// K5a: greedy cache pass, one warp per image
+// K5a: greedy cache pass, one warp per image, working set in global memory (fallback for images whose
+// busiest level does not fit the shared-memory pools of k_dedup_smem below)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32)
 k_dedup(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ cand, const unsigned int* __restrict__ level_off,
@@ -42,6 +45,7 @@ k_dedup(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ cand,
         if (lane == 0) n_cache[img] = 0;
         return;
     }
+    if (image_fits_smem_pass(plan, lo)) return;  // handled by k_dedup_smem
     unsigned int n = 0;  // cache length (uniform across lanes)
     bool overflow = false;
 
@@ -145,6 +149,197 @@ k_dedup(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ cand,
             }
         }
     }
+    if (lane == 0) {
+        n_cache[img] = n;
+        if (overflow) atomicOr(&err_flags[img], (unsigned int)kErrKpOverflow);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5a': the same greedy pass with the whole working set in shared memory. Only keypoints of classes
+// L-1 and L can match a level-L candidate, so two pools (by class parity) of at most kPool entries
+// each hold everything the pass touches; a pool is flushed to the global cache arrays (indexed by
+// slot) when its class falls out of reach. Hash-grid heads are u16 pool indices. An image whose
+// busiest level has more than kPool candidates is left to the global-memory kernel above.
+// ------------------------------------------------------------------------------------------------
+constexpr int kPool = 4096;
+constexpr int kMaxGridCells = 8448;
+constexpr unsigned short kNil = 0xffffu;
+
+__device__ __forceinline__ bool image_fits_smem_pass(const PlanDev* plan, const unsigned int* lo) {
+    if (plan->grid_w * plan->grid_h > kMaxGridCells) return false;
+    for (int l = 0; l < plan->n_levels; l++)
+        if (lo[l + 1] - lo[l] > (unsigned int)kPool) return false;
+    return true;
+}
+
+struct DedupSmem {
+    float px[2][kPool];
+    float py[2][kPool];
+    float presp[2][kPool];
+    unsigned int pslot[2][kPool];  // global cache slot; 0xffffffff = dead (replaced)
+    unsigned short pnext[2][kPool];
+    unsigned short heads[2][kMaxGridCells];
+};
+
+__global__ void __launch_bounds__(32)
+k_dedup_smem(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ cand, const unsigned int* __restrict__ level_off,
+             const float* __restrict__ ldet_plane, int batch, unsigned int cand_cap, unsigned int kp_cap, float* __restrict__ c_x,
+             float* __restrict__ c_y, float* __restrict__ c_resp, int* __restrict__ c_cls, unsigned int* __restrict__ n_cache,
+             unsigned int* __restrict__ err_flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    DedupSmem& S = *reinterpret_cast<DedupSmem*>(smem_raw);
+    const int img = blockIdx.x;
+    const int lane = threadIdx.x;
+    const unsigned int FULL = 0xffffffffu;
+    const unsigned int* cl = cand + (size_t)img * cand_cap;
+    const unsigned int* lo = level_off + (size_t)img * (kMaxLevels + 1);
+    if (err_flags[img] & kErrCandOverflow) {
+        if (lane == 0) n_cache[img] = 0;
+        return;
+    }
+    if (!image_fits_smem_pass(plan, lo)) return;  // handled by k_dedup
+    const int gw = plan->grid_w, gh = plan->grid_h, gshift = plan->grid_shift;
+    const int gcells = gw * gh;
+    c_x += (size_t)img * kp_cap;
+    c_y += (size_t)img * kp_cap;
+    c_resp += (size_t)img * kp_cap;
+    c_cls += (size_t)img * kp_cap;
+    unsigned int n = 0;
+    int cnt[2] = {0, 0};
+    bool overflow = false;
+
+    auto flush = [&](int which, int cls) {
+        for (int i = lane; i < cnt[which]; i += 32) {
+            const unsigned int s = S.pslot[which][i];
+            if (s != 0xffffffffu) {
+                c_x[s] = S.px[which][i];
+                c_y[s] = S.py[which][i];
+                c_resp[s] = S.presp[which][i];
+                c_cls[s] = cls;
+            }
+        }
+    };
+
+    const int nl = plan->n_levels;
+    for (int L = 0; L < nl && !overflow; L++) {
+        const LevelDev& lv = plan->lv[L];
+        const int cur = L & 1, prv = cur ^ 1;
+        if (L >= 2) flush(cur, L - 2);  // class L-2 can no longer be matched or replaced
+        cnt[cur] = 0;
+        for (int i = lane; i < gcells; i += 32) S.heads[cur][i] = kNil;
+        __syncwarp();
+        const float ratio = lv.ratio, size = lv.kp_size, size_sq = lv.size_sq, hr = lv.half_ratio_m1;
+        const float* ldet = ldet_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
+        const unsigned int beg = lo[L], end = lo[L + 1];
+        // software-pipelined prefetch of 32 candidates (flat index + |Ldet|)
+        unsigned int nx_flat = 0;
+        float nx_resp = 0.0f;
+        if (beg + lane < end) {
+            nx_flat = cl[beg + lane];
+            nx_resp = fabsf(ldet[nx_flat]);
+        }
+        for (unsigned int base = beg; base < end && !overflow; base += 32) {
+            const unsigned int my_flat = nx_flat;
+            const float my_resp = nx_resp;
+            if (base + 32 + lane < end) {
+                nx_flat = cl[base + 32 + lane];
+                nx_resp = fabsf(ldet[nx_flat]);
+            }
+            const int n_here = min(32u, end - base);
+            for (int k = 0; k < n_here; k++) {
+                const unsigned int flat = __shfl_sync(FULL, my_flat, k);
+                const float resp = __shfl_sync(FULL, my_resp, k);
+                const int px = (int)(flat % (unsigned int)lv.w), py = (int)(flat / (unsigned int)lv.w);
+                const float qx = (float)px * ratio, qy = (float)py * ratio;
+                const int cx0 = max(0, ((int)floorf(qx - size) - 1) >> gshift);
+                const int cx1 = min(gw - 1, ((int)floorf(qx + size) + 1) >> gshift);
+                const int cy0 = max(0, ((int)floorf(qy - size) - 1) >> gshift);
+                const int cy1 = min(gh - 1, ((int)floorf(qy + size) + 1) >> gshift);
+                const int nx = cx1 - cx0 + 1;
+                const int ncell = nx * (cy1 - cy0 + 1);
+                const int ntot = (L > 0) ? 2 * ncell : ncell;
+                unsigned int best = 0xffffffffu;  // lowest matching slot
+                unsigned int best_ref = 0;        // (pool << 16) | pool index of that slot
+                for (int c = lane; c < ntot; c += 32) {
+                    const int which = (c >= ncell) ? prv : cur;
+                    const int cc = (c >= ncell) ? c - ncell : c;
+                    const int cell = (cy0 + cc / nx) * gw + (cx0 + cc % nx);
+                    unsigned short e = S.heads[which][cell];
+                    while (e != kNil) {
+                        const float dx = qx - S.px[which][e], dy = qy - S.py[which][e];
+                        const float dist = dx * dx + dy * dy;
+                        const unsigned int s = S.pslot[which][e];
+                        if (dist <= size_sq && s < best) {
+                            best = s;
+                            best_ref = ((unsigned int)which << 16) | e;
+                        }
+                        e = S.pnext[which][e];
+                    }
+                }
+                const unsigned int gbest = __reduce_min_sync(FULL, best);
+                bool append = false;
+                unsigned int slot = 0;
+                if (gbest == 0xffffffffu) {
+                    if (n >= kp_cap) {
+                        overflow = true;
+                        break;
+                    }
+                    slot = n++;
+                    append = true;
+                } else {
+                    // the lane that found the winning slot publishes where it lives
+                    const unsigned int owner = __ffs(__ballot_sync(FULL, best == gbest)) - 1;
+                    const unsigned int ref = __shfl_sync(FULL, best_ref, owner);
+                    const int bw = (int)(ref >> 16);
+                    const unsigned short be = (unsigned short)(ref & 0xffffu);
+                    if (resp > S.presp[bw][be]) {  // scale_space_extrema.rs:67
+                        slot = gbest;
+                        append = true;
+                        if (lane == 0) {
+                            // unlink the old occupant from its cell list and mark it dead
+                            const int ocx = min(gw - 1, max(0, (int)S.px[bw][be] >> gshift));
+                            const int ocy = min(gh - 1, max(0, (int)S.py[bw][be] >> gshift));
+                            const int ocell = ocy * gw + ocx;
+                            unsigned short e = S.heads[bw][ocell];
+                            if (e == be) {
+                                S.heads[bw][ocell] = S.pnext[bw][be];
+                            } else {
+                                while (e != kNil) {
+                                    const unsigned short nxt = S.pnext[bw][e];
+                                    if (nxt == be) {
+                                        S.pnext[bw][e] = S.pnext[bw][be];
+                                        break;
+                                    }
+                                    e = nxt;
+                                }
+                            }
+                            S.pslot[bw][be] = 0xffffffffu;
+                        }
+                    }
+                }
+                if (append) {
+                    const int at = cnt[cur]++;  // <= candidates of this level <= kPool
+                    if (lane == 0) {
+                        const float fx = (float)px * ratio + hr, fy = (float)py * ratio + hr;  // :89-92
+                        S.px[cur][at] = fx;
+                        S.py[cur][at] = fy;
+                        S.presp[cur][at] = resp;
+                        S.pslot[cur][at] = slot;
+                        const int ncx = min(gw - 1, max(0, (int)fx >> gshift));
+                        const int ncy = min(gh - 1, max(0, (int)fy >> gshift));
+                        const int ncl = ncy * gw + ncx;
+                        S.pnext[cur][at] = S.heads[cur][ncl];
+                        S.heads[cur][ncl] = (unsigned short)at;
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
+    // flush what is still resident: classes nl-2 (if any) and nl-1
+    if (nl >= 2) flush((nl - 2) & 1, nl - 2);
+    flush((nl - 1) & 1, nl - 1);
     if (lane == 0) {
         n_cache[img] = n;
         if (overflow) atomicOr(&err_flags[img], (unsigned int)kErrKpOverflow);
@@ -445,10 +640,17 @@ k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plan
 
 }  // namespace
 
+cudaError_t init_keypoint_attributes() {
+    return cudaFuncSetAttribute(k_dedup_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DedupSmem));
+}
+
 int launch_dedup(const Launch& L, const Plan& P, const Buffers& B) {
+    // every image is handled by exactly one of the two kernels (image_fits_smem_pass)
+    k_dedup_smem<<<L.batch, 32, sizeof(DedupSmem), L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap,
+                                                                L.kp_cap, B.c_x, B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags);
     k_dedup<<<L.batch, 32, 0, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap, L.kp_cap,
                                            B.c_x, B.c_y, B.c_resp, B.c_cls, B.c_next, B.grid, B.n_cache, B.err_flags);
-    return 1;
+    return 2;
 }
 
 int launch_finalize(const Launch& L, const Plan& P, const Buffers& B) {

@@ -167,3 +167,21 @@ def synthetic_image(h, w, seed, n_rect=None):
         img[y0:y0 + rh, x0:x0 + rw] = rng.uniform(0, 255)
     img = gaussian_filter(img, 0.7)
     return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def natural_image(h, w, seed):
+    """Photo-like density (bench.py's workload recipe in numpy): five octaves of blurred noise with
+    amplitudes (4,8,16,32,48) at sigma (1.5,3,6,12,24), 48 rectangles per 2 Mpx, sigma-1 blur."""
+    from scipy.ndimage import gaussian_filter
+    rng = np.random.Generator(np.random.PCG64(seed))
+    img = np.full((h, w), 128.0)
+    for a, s in zip((4, 8, 16, 32, 48), (1.5, 3, 6, 12, 24)):
+        n = gaussian_filter(rng.standard_normal((h, w)), s)
+        img += a * n / n.std()
+    for _ in range(max(2, int(round(48 * h * w / (1920.0 * 1080.0))))):
+        rw, rh = rng.integers(8, 121, size=2)
+        x0 = rng.integers(0, max(1, w - 8))
+        y0 = rng.integers(0, max(1, h - 8))
+        img[y0:y0 + rh, x0:x0 + rw] = rng.uniform(0, 255)
+    img = gaussian_filter(img, 1.0)
+    return np.clip(img, 0, 255).astype(np.uint8)

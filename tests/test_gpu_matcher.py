@@ -80,9 +80,12 @@ def test_sharded_device_path_matches_unsharded(engine, oracle, akz):
     full = oracle.match_top2(q, db, desc_len=61)
     for world in (1, 2, 3, 8):
         parts = torch.zeros((world, len(q)), dtype=torch.int64, device="cuda")  # 8-byte akz_top2 records
+        keep_alive = []  # the engine runs on its own stream: torch must not recycle a shard while it is in use
         for r in range(world):
             lo, hi = shard_range(len(db), world, r)
             ddb = _dev(db[lo:hi]) if hi > lo else torch.zeros((1, 64), dtype=torch.uint8, device="cuda")
+            keep_alive.append(ddb)
+            torch.cuda.synchronize()
             engine.match_top2_device(dq.data_ptr(), len(q), ddb.data_ptr(), hi - lo, parts[r].data_ptr(), db_index_base=lo)
         out = torch.zeros(len(q), dtype=torch.int64, device="cuda")
         engine.merge_top2_device(parts.data_ptr(), world, len(q), out.data_ptr())

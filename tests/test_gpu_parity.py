@@ -71,6 +71,12 @@ def test_extract_flat_and_noise(engine, oracle):
     ref = oracle.extract(oracle.unit_float_from_u8(noise))
     check_against_oracle(f, ref)
     assert len(ref.keypoints) > 50
+    # > 4096 candidates on one level: the cache pass falls back from shared to global memory
+    big = rng.integers(0, 256, (600, 800), dtype=np.uint8)
+    f = engine.extract_u8(big)
+    ref = oracle.extract(oracle.unit_float_from_u8(big), threads=8)
+    check_against_oracle(f, ref, evolutions=False)
+    assert np.bincount(ref.keypoints["class_id"]).max() > 4096
 
 
 def test_f32_entry_equals_u8_entry(engine, oracle):
