@@ -31,7 +31,15 @@ struct DetParams {
     float thr;
     int xmin, xmax, ymin, ymax;
     int wpr;
+    int fast;  // interior 64x32 tiles are computed by k_detector_fast
 };
+
+// 64x32 tile (i,j) lies far enough inside the image that no pass clamps and every halo load is in range
+__device__ __forceinline__ bool fast_tile_interior(int i, int j, int W, int H, int s) {
+    const int m = 4 * s + 4;
+    const int x0 = i * 64, y0 = j * 32;
+    return x0 >= m && x0 + 64 + m <= W && y0 >= m && y0 + 32 + m <= H;
+}
 
 __global__ void __launch_bounds__(NTX* NTY)
 k_detector(const float* __restrict__ lsmooth, size_t img_px, float* __restrict__ oLx, float* __restrict__ oLy,
@@ -49,6 +57,7 @@ k_detector(const float* __restrict__ lsmooth, size_t img_px, float* __restrict__
     float* b4 = b3 + N;
     const int tx0 = min((int)blockIdx.x * DT, W - DT);
     const int ty0 = min((int)blockIdx.y * DT, H - DT);
+    if (p.fast && tx0 == (int)blockIdx.x * DT && ty0 == (int)blockIdx.y * DT && fast_tile_interior(tx0 / 64, ty0 / 32, W, H, s)) return;
     const int img = blockIdx.z;
     auto idx = [&](int x, int y) { return (y - ty0 + HL) * PW + (x - tx0 + HL); };
     const float* L = lsmooth + (size_t)img * img_px;
@@ -155,6 +164,180 @@ k_detector(const float* __restrict__ lsmooth, size_t img_px, float* __restrict__
                 const int w0 = tx0 >> 5, sh = tx0 & 31;
                 atomicOr(&m[(size_t)y * p.wpr + w0], bal << sh);
                 if (sh != 0 && (bal >> (32 - sh)) != 0) atomicOr(&m[(size_t)y * p.wpr + w0 + 1], bal >> (32 - sh));
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fast path: interior 64x32 tiles, compile-time Scharr scale S, every shared-memory access a float4
+// (4 pixels per thread), no clamp arithmetic. Same operation order as k_detector -> same bits.
+// ------------------------------------------------------------------------------------------------
+template <int S>
+struct DetGeo {
+    // x halos are multiples of 4 so that every access is an aligned float4: Ldet is produced on
+    // [-4, 68) (needs [-1, 65)), so Lx/Ly are needed on [-4-S, 68+S) and Lsmooth S further out
+    static constexpr int HX1 = ((4 + S) + 3) & ~3;      // x halo of A/Bo/Lx/Ly
+    static constexpr int HLX = ((HX1 + S) + 3) & ~3;    // x halo of the Lsmooth tile
+    static constexpr int HLY = 2 * S + 1;
+    static constexpr int HY2 = S + 1;                   // y halo of Lx/Ly/C/D/E
+    static constexpr int P0 = 64 + 2 * HLX, R0 = 32 + 2 * HLY;
+    static constexpr int P1 = 64 + 2 * HX1, R2 = 32 + 2 * HY2;
+    static constexpr int N0 = P0 * R0, N1 = P1 * R0, N2 = P1 * R2;
+    static constexpr int FLOATS = N0 + 2 * N1 + 2 * N2;
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+
+// 12 consecutive values v[0..11] = in[x-4 .. x+7]; main-axis taps of outputs x..x+3 (tap order -S, 0, +S)
+template <int S>
+__device__ __forceinline__ float4 hmain(const float (&v)[12], float n, float wn) {
+    float4 r;
+    r.x = (n * v[4 - S] + wn * v[4]) + n * v[4 + S];
+    r.y = (n * v[5 - S] + wn * v[5]) + n * v[5 + S];
+    r.z = (n * v[6 - S] + wn * v[6]) + n * v[6 + S];
+    r.w = (n * v[7 - S] + wn * v[7]) + n * v[7 + S];
+    return r;
+}
+template <int S>
+__device__ __forceinline__ float4 hoff(const float (&v)[12]) {
+    return make_float4(v[4 + S] - v[4 - S], v[5 + S] - v[5 - S], v[6 + S] - v[6 - S], v[7 + S] - v[7 - S]);
+}
+__device__ __forceinline__ void load12(const float* row, int cx, float (&v)[12]) {
+    const float4 a = ld4(row + cx - 4), b = ld4(row + cx), c = ld4(row + cx + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+}
+__device__ __forceinline__ float4 vmain(const float4& a, const float4& b, const float4& c, float n, float wn) {
+    return make_float4((n * a.x + wn * b.x) + n * c.x, (n * a.y + wn * b.y) + n * c.y, (n * a.z + wn * b.z) + n * c.z,
+                       (n * a.w + wn * b.w) + n * c.w);
+}
+__device__ __forceinline__ float4 sub4(const float4& a, const float4& b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
+
+template <int S>
+__global__ void __launch_bounds__(256)
+k_detector_fast(const float* __restrict__ lsmooth, size_t img_px, float* __restrict__ oLx, float* __restrict__ oLy,
+                float* __restrict__ oLdet, float* __restrict__ oLxx, float* __restrict__ oLyy, float* __restrict__ oLxy,
+                unsigned int* __restrict__ mask, size_t mask_img_words, DetParams p) {
+    using G = DetGeo<S>;
+    extern __shared__ __align__(16) float smem[];
+    const int W = p.W, H = p.H;
+    if (!fast_tile_interior(blockIdx.x, blockIdx.y, W, H, S)) return;
+    float* b0 = smem;
+    float* b1 = b0 + G::N0;
+    float* b2 = b1 + G::N1;
+    float* b3 = b2 + G::N1;
+    float* b4 = b3 + G::N2;
+    const int x0 = blockIdx.x * 64, y0 = blockIdx.y * 32;
+    const int img = blockIdx.z;
+    const int tid = threadIdx.x;
+    const float n = p.n, wn = p.wn;
+    const size_t ibase = (size_t)img * img_px;
+
+    {  // stage 0: Lsmooth rows y0-HLY.., cols x0-HLX.. (P0 wide) -> b0
+        const float* L = lsmooth + ibase + (size_t)(y0 - G::HLY) * W + (x0 - G::HLX);
+        constexpr int GW = G::P0 / 4;
+        for (int g = tid; g < GW * G::R0; g += 256) {
+            const int gy = g / GW, gx = g - gy * GW;
+            st4(b0 + gy * G::P0 + 4 * gx, ld4(L + (size_t)gy * W + 4 * gx));
+        }
+    }
+    __syncthreads();
+    {  // stage 1: A = H_main(L) -> b1, Bo = H_off(L) -> b2 : cols x0-HX1.. (P1 wide), all R0 rows
+        constexpr int GW = G::P1 / 4;
+        for (int g = tid; g < GW * G::R0; g += 256) {
+            const int gy = g / GW, gx = g - gy * GW;
+            float v[12];
+            load12(b0 + gy * G::P0, G::HLX - G::HX1 + 4 * gx, v);
+            st4(b1 + gy * G::P1 + 4 * gx, hmain<S>(v, n, wn));
+            st4(b2 + gy * G::P1 + 4 * gx, hoff<S>(v));
+        }
+    }
+    __syncthreads();
+    {  // stage 2: Lx = V_off(A) -> b3, Ly = V_main(Bo) -> b4 : rows y0-HY2.. (R2 rows)
+        constexpr int GW = G::P1 / 4;
+        float* ox = oLx + ibase;
+        float* oy = oLy + ibase;
+        for (int g = tid; g < GW * G::R2; g += 256) {
+            const int gy = g / GW, gx = g - gy * GW;
+            const int ry = gy + (G::HLY - G::HY2);  // row in b1/b2
+            const float* a = b1 + ry * G::P1 + 4 * gx;
+            const float* b = b2 + ry * G::P1 + 4 * gx;
+            const float4 lx = sub4(ld4(a + S * G::P1), ld4(a - S * G::P1));
+            const float4 ly = vmain(ld4(b - S * G::P1), ld4(b), ld4(b + S * G::P1), n, wn);
+            st4(b3 + gy * G::P1 + 4 * gx, lx);
+            st4(b4 + gy * G::P1 + 4 * gx, ly);
+            const int lxp = 4 * gx - G::HX1, lyp = gy - G::HY2;  // tile-local position of the group
+            if (lxp >= 0 && lxp < 64 && lyp >= 0 && lyp < 32) {
+                const size_t o = (size_t)(y0 + lyp) * W + x0 + lxp;
+                st4(ox + o, lx);
+                st4(oy + o, ly);
+            }
+        }
+    }
+    __syncthreads();
+    {  // stage 3: C = H_main(Lx) -> b0, D = H_off(Ly) -> b1, E = H_off(Lx) -> b2 : cols x0-4.. (72 wide), R2 rows
+        constexpr int GW = 72 / 4;
+        for (int g = tid; g < GW * G::R2; g += 256) {
+            const int gy = g / GW, gx = g - gy * GW;
+            float v[12];
+            load12(b3 + gy * G::P1, G::HX1 - 4 + 4 * gx, v);
+            st4(b0 + gy * G::P0 + 4 * gx, hmain<S>(v, n, wn));
+            st4(b2 + gy * G::P1 + 4 * gx, hoff<S>(v));
+            load12(b4 + gy * G::P1, G::HX1 - 4 + 4 * gx, v);
+            st4(b1 + gy * G::P1 + 4 * gx, hoff<S>(v));
+        }
+    }
+    __syncthreads();
+    {  // stage 4: Ldet over cols x0-4.. (72 wide), rows y0-1.. (34 rows) -> b3
+        constexpr int GW = 72 / 4;
+        float* od = oLdet + ibase;
+        for (int g = tid; g < GW * 34; g += 256) {
+            const int gy = g / GW, gx = g - gy * GW;
+            const int ry = gy + (G::HY2 - 1);  // row in b0/b1/b2 (stage-3 rows)
+            const float* c = b0 + ry * G::P0 + 4 * gx;
+            const float* d = b1 + ry * G::P1 + 4 * gx;
+            const float* e = b2 + ry * G::P1 + 4 * gx;
+            const float4 lxx = sub4(ld4(c + S * G::P0), ld4(c - S * G::P0));
+            const float4 lyy = vmain(ld4(d - S * G::P1), ld4(d), ld4(d + S * G::P1), n, wn);
+            const float4 lxy = vmain(ld4(e - S * G::P1), ld4(e), ld4(e + S * G::P1), n, wn);
+            float4 det;  // detector_response.rs:52
+            det.x = ((lxx.x * lyy.x) - (lxy.x * lxy.x)) * p.quat;
+            det.y = ((lxx.y * lyy.y) - (lxy.y * lxy.y)) * p.quat;
+            det.z = ((lxx.z * lyy.z) - (lxy.z * lxy.z)) * p.quat;
+            det.w = ((lxx.w * lyy.w) - (lxy.w * lxy.w)) * p.quat;
+            st4(b3 + gy * G::P1 + 4 * gx, det);
+            const int lxp = 4 * gx - 4, lyp = gy - 1;
+            if (lxp >= 0 && lxp < 64 && lyp >= 0 && lyp < 32) {
+                const size_t o = (size_t)(y0 + lyp) * W + x0 + lxp;
+                st4(od + o, det);
+                if (oLxx != nullptr) {
+                    st4(oLxx + ibase + o, lxx);
+                    st4(oLyy + ibase + o, lyy);
+                    st4(oLxy + ibase + o, lxy);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    {  // stage 5: threshold + strict 4-neighbour maximum + is_out; b3 holds Ldet at (col lx+4, row ly+1)
+        unsigned int* m = mask + (size_t)img * mask_img_words;
+        const int lane = tid & 31, wid = tid >> 5;
+        for (int ly = wid; ly < 32; ly += 8) {
+            const int y = y0 + ly;
+#pragma unroll
+            for (int hx = 0; hx < 2; hx++) {
+                const int lx = lane + 32 * hx, x = x0 + lx;
+                bool cand = false;
+                if (x >= p.xmin && x <= p.xmax && y >= p.ymin && y <= p.ymax) {
+                    const float* q = b3 + (ly + 1) * G::P1 + lx + 4;
+                    const float v = q[0];
+                    cand = v > p.thr && v > q[1] && v > q[-1] && v > q[-G::P1] && v > q[G::P1];
+                }
+                const unsigned int bal = __ballot_sync(0xffffffffu, cand);
+                if (bal != 0 && lane == 0) atomicOr(&m[(size_t)y * p.wpr + (x0 >> 5) + hx], bal);
             }
         }
     }
@@ -279,7 +462,13 @@ __global__ void k_scatter(const unsigned int* __restrict__ mask, const PlanDev* 
 // opt in to > 48 KB dynamic shared memory (call once per device, after cudaSetDevice)
 cudaError_t init_detector_attributes() {
     const int pw = DT + 2 * (2 * kMaxDetScale + 1);
-    return cudaFuncSetAttribute(k_detector, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * pw * pw * (int)sizeof(float));
+    cudaError_t e = cudaFuncSetAttribute(k_detector, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * pw * pw * (int)sizeof(float));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_detector_fast<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DetGeo<2>::FLOATS * (int)sizeof(float));
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_detector_fast<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DetGeo<3>::FLOATS * (int)sizeof(float));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_detector_fast<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, DetGeo<4>::FLOATS * (int)sizeof(float));
 }
 
 int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level) {
@@ -298,17 +487,34 @@ int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level)
     p.ymin = lv.ymin;
     p.ymax = lv.ymax;
     p.wpr = lv.wpr;
+    const size_t img_px = (size_t)lv.w * lv.h;
+    // float4 fast path for interior tiles: rows and image slabs must be 16-byte aligned
+    p.fast = (lv.w % 4 == 0 && img_px % 4 == 0 && lv.s_det >= 2 && lv.s_det <= 4 && lv.w >= 64 + 2 * (4 * lv.s_det + 4) &&
+              lv.h >= 32 + 2 * (4 * lv.s_det + 4)) ? 1 : 0;
     const int HL = 2 * lv.s_det + 1, PW = DT + 2 * HL;
     const size_t smem = (size_t)5 * PW * PW * sizeof(float);
-    const size_t img_px = (size_t)lv.w * lv.h;
     const size_t off = (size_t)lv.off * L.batch;
     // level 0: Lsmooth is Lt (lib.rs:58)
     const float* ls = (level == 0) ? B.Lt : (B.keep ? B.Lsmooth + off : B.Lsmooth);
+    float* xx = B.keep ? B.Lxx + off : nullptr;
+    float* yy = B.keep ? B.Lyy + off : nullptr;
+    float* xy = B.keep ? B.Lxy + off : nullptr;
+    unsigned int* mk = B.mask + lv.mask_off;
+    int launches = 0;
+    if (p.fast) {
+        dim3 gf(lv.w / 64, lv.h / 32, L.batch);
+        if (lv.s_det == 2)
+            k_detector_fast<2><<<gf, 256, DetGeo<2>::FLOATS * sizeof(float), L.stream>>>(ls, img_px, B.Lx + off, B.Ly + off, B.Ldet + off, xx, yy, xy, mk, (size_t)P.dev.mask_words, p);
+        else if (lv.s_det == 3)
+            k_detector_fast<3><<<gf, 256, DetGeo<3>::FLOATS * sizeof(float), L.stream>>>(ls, img_px, B.Lx + off, B.Ly + off, B.Ldet + off, xx, yy, xy, mk, (size_t)P.dev.mask_words, p);
+        else
+            k_detector_fast<4><<<gf, 256, DetGeo<4>::FLOATS * sizeof(float), L.stream>>>(ls, img_px, B.Lx + off, B.Ly + off, B.Ldet + off, xx, yy, xy, mk, (size_t)P.dev.mask_words, p);
+        launches++;
+    }
     dim3 grid((lv.w + DT - 1) / DT, (lv.h + DT - 1) / DT, L.batch);
-    k_detector<<<grid, dim3(NTX, NTY), smem, L.stream>>>(
-        ls, img_px, B.Lx + off, B.Ly + off, B.Ldet + off, B.keep ? B.Lxx + off : nullptr, B.keep ? B.Lyy + off : nullptr,
-        B.keep ? B.Lxy + off : nullptr, B.mask + lv.mask_off, (size_t)P.dev.mask_words, p);
-    return 1;
+    k_detector<<<grid, dim3(NTX, NTY), smem, L.stream>>>(ls, img_px, B.Lx + off, B.Ly + off, B.Ldet + off, xx, yy, xy, mk,
+                                                         (size_t)P.dev.mask_words, p);
+    return launches + 1;
 }
 
 int launch_compact(const Launch& L, const Plan& P, const Buffers& B) {
