@@ -15,6 +15,7 @@
 // written as one bit per pixel; a second set of kernels turns the bitmask into a list in raster order,
 // which the order-dependent cache pass of the reference needs.
 #include "common.cuh"
+#include "tile_util.cuh"
 
 namespace akz {
 namespace {
@@ -34,13 +35,6 @@ struct DetParams {
     int fast;  // interior 64x32 tiles are computed by k_detector_fast
 };
 
-// 64x32 tile (i,j) lies far enough inside the image that no pass clamps and every halo load is in range
-__device__ __forceinline__ bool fast_tile_interior(int i, int j, int W, int H, int s) {
-    const int m = 4 * s + 4;
-    const int x0 = i * 64, y0 = j * 32;
-    return x0 >= m && x0 + 64 + m <= W && y0 >= m && y0 + 32 + m <= H;
-}
-
 __global__ void __launch_bounds__(NTX* NTY)
 k_detector(const float* __restrict__ lsmooth, size_t img_px, float* __restrict__ oLx, float* __restrict__ oLy,
            float* __restrict__ oLdet, float* __restrict__ oLxx, float* __restrict__ oLyy, float* __restrict__ oLxy,
@@ -57,7 +51,6 @@ k_detector(const float* __restrict__ lsmooth, size_t img_px, float* __restrict__
     float* b4 = b3 + N;
     const int tx0 = min((int)blockIdx.x * DT, W - DT);
     const int ty0 = min((int)blockIdx.y * DT, H - DT);
-    if (p.fast && tx0 == (int)blockIdx.x * DT && ty0 == (int)blockIdx.y * DT && fast_tile_interior(tx0 / 64, ty0 / 32, W, H, s)) return;
     const int img = blockIdx.z;
     auto idx = [&](int x, int y) { return (y - ty0 + HL) * PW + (x - tx0 + HL); };
     const float* L = lsmooth + (size_t)img * img_px;
@@ -187,9 +180,6 @@ struct DetGeo {
     static constexpr int FLOATS = N0 + 2 * N1 + 2 * N2;
 };
 
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
-
 // 12 consecutive values v[0..11] = in[x-4 .. x+7]; main-axis taps of outputs x..x+3 (tap order -S, 0, +S)
 template <int S>
 __device__ __forceinline__ float4 hmain(const float (&v)[12], float n, float wn) {
@@ -204,140 +194,165 @@ template <int S>
 __device__ __forceinline__ float4 hoff(const float (&v)[12]) {
     return make_float4(v[4 + S] - v[4 - S], v[5 + S] - v[5 - S], v[6 + S] - v[6 - S], v[7 + S] - v[7 - S]);
 }
-__device__ __forceinline__ void load12(const float* row, int cx, float (&v)[12]) {
-    const float4 a = ld4(row + cx - 4), b = ld4(row + cx), c = ld4(row + cx + 4);
-    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-    v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
-}
 __device__ __forceinline__ float4 vmain(const float4& a, const float4& b, const float4& c, float n, float wn) {
     return make_float4((n * a.x + wn * b.x) + n * c.x, (n * a.y + wn * b.y) + n * c.y, (n * a.z + wn * b.z) + n * c.z,
                        (n * a.w + wn * b.w) + n * c.w);
 }
-__device__ __forceinline__ float4 sub4(const float4& a, const float4& b) { return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w); }
-
 template <int S>
 __global__ void __launch_bounds__(256)
 k_detector_fast(const float* __restrict__ lsmooth, size_t img_px, float* __restrict__ oLx, float* __restrict__ oLy,
-                float* __restrict__ oLdet, float* __restrict__ oLxx, float* __restrict__ oLyy, float* __restrict__ oLxy,
-                unsigned int* __restrict__ mask, size_t mask_img_words, DetParams p) {
+                float* __restrict__ oLdet, unsigned int* __restrict__ mask, size_t mask_img_words, DetParams p) {
     using G = DetGeo<S>;
     extern __shared__ __align__(16) float smem[];
     const int W = p.W, H = p.H;
-    if (!fast_tile_interior(blockIdx.x, blockIdx.y, W, H, S)) return;
     float* b0 = smem;
     float* b1 = b0 + G::N0;
     float* b2 = b1 + G::N1;
     float* b3 = b2 + G::N1;
     float* b4 = b3 + G::N2;
-    const int x0 = blockIdx.x * 64, y0 = blockIdx.y * 32;
+    // full-size tiles, the last one of a row/column shifted inwards (x0 stays a multiple of 4: W % 4 == 0)
+    const int x0 = min((int)blockIdx.x * 64, W - 64), y0 = min((int)blockIdx.y * 32, H - 32);
     const int img = blockIdx.z;
     const int tid = threadIdx.x;
     const float n = p.n, wn = p.wn;
     const size_t ibase = (size_t)img * img_px;
+    // does any stage region leave the image or touch a clamp band? (block-uniform)
+    const bool border = x0 - G::HLX < S || x0 + 64 + G::HLX > W - S || y0 - G::HLY < S || y0 + 32 + G::HLY > H - S;
 
-    {  // stage 0: Lsmooth rows y0-HLY.., cols x0-HLX.. (P0 wide) -> b0
-        const float* L = lsmooth + ibase + (size_t)(y0 - G::HLY) * W + (x0 - G::HLX);
-        constexpr int GW = G::P0 / 4;
-        for (int g = tid; g < GW * G::R0; g += 256) {
-            const int gy = g / GW, gx = g - gy * GW;
-            st4(b0 + gy * G::P0 + 4 * gx, ld4(L + (size_t)gy * W + 4 * gx));
+    {  // stage 0: Lsmooth rows y0-HLY.., cols x0-HLX.. (P0 wide) -> b0 (out-of-image groups are never read by valid outputs)
+        const float* L = lsmooth + ibase;
+        constexpr int GW = G::P0 / 4, TOT = GW * G::R0, IT = (TOT + 255) / 256;
+#pragma unroll
+        for (int it = 0; it < IT; it++) {
+            const int g = tid + 256 * it;
+            if (g < TOT) {
+                const int gy = g / GW, gx = g - gy * GW;
+                const int y = y0 - G::HLY + gy, x = x0 - G::HLX + 4 * gx;
+                float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (!border || (y >= 0 && y < H && x >= 0 && x < W)) v = ld4(L + (size_t)y * W + x);
+                st4(b0 + gy * G::P0 + 4 * gx, v);
+            }
         }
     }
     __syncthreads();
     {  // stage 1: A = H_main(L) -> b1, Bo = H_off(L) -> b2 : cols x0-HX1.. (P1 wide), all R0 rows
-        constexpr int GW = G::P1 / 4;
-        for (int g = tid; g < GW * G::R0; g += 256) {
-            const int gy = g / GW, gx = g - gy * GW;
-            float v[12];
-            load12(b0 + gy * G::P0, G::HLX - G::HX1 + 4 * gx, v);
-            st4(b1 + gy * G::P1 + 4 * gx, hmain<S>(v, n, wn));
-            st4(b2 + gy * G::P1 + 4 * gx, hoff<S>(v));
+        constexpr int GW = G::P1 / 4, TOT = GW * G::R0, IT = (TOT + 255) / 256;
+#pragma unroll
+        for (int it = 0; it < IT; it++) {
+            const int g = tid + 256 * it;
+            if (g < TOT) {
+                const int gy = g / GW, gx = g - gy * GW;
+                float v[12];
+                load12(b0 + gy * G::P0, G::HLX - G::HX1 + 4 * gx, v);
+                st4(b1 + gy * G::P1 + 4 * gx, hmain<S>(v, n, wn));
+                st4(b2 + gy * G::P1 + 4 * gx, hoff<S>(v));
+            }
         }
     }
     __syncthreads();
+    if (border) {
+        fix_border(b1, G::P1, x0 - G::HX1, y0 - G::HLY, G::P1, G::R0, W, H, S, tid, 256);
+        fix_border(b2, G::P1, x0 - G::HX1, y0 - G::HLY, G::P1, G::R0, W, H, S, tid, 256);
+    }
     {  // stage 2: Lx = V_off(A) -> b3, Ly = V_main(Bo) -> b4 : rows y0-HY2.. (R2 rows)
-        constexpr int GW = G::P1 / 4;
+        constexpr int GW = G::P1 / 4, TOT = GW * G::R2, IT = (TOT + 255) / 256;
+#pragma unroll
+        for (int it = 0; it < IT; it++) {
+            const int g = tid + 256 * it;
+            if (g < TOT) {
+                const int gy = g / GW, gx = g - gy * GW;
+                const int ry = gy + (G::HLY - G::HY2);  // row in b1/b2
+                const float* a = b1 + ry * G::P1 + 4 * gx;
+                const float* b = b2 + ry * G::P1 + 4 * gx;
+                st4(b3 + gy * G::P1 + 4 * gx, sub4(ld4(a + S * G::P1), ld4(a - S * G::P1)));
+                st4(b4 + gy * G::P1 + 4 * gx, vmain(ld4(b - S * G::P1), ld4(b), ld4(b + S * G::P1), n, wn));
+            }
+        }
+    }
+    __syncthreads();
+    if (border) {
+        fix_border(b3, G::P1, x0 - G::HX1, y0 - G::HY2, G::P1, G::R2, W, H, S, tid, 256);
+        fix_border(b4, G::P1, x0 - G::HX1, y0 - G::HY2, G::P1, G::R2, W, H, S, tid, 256);
+    }
+    {  // stage 3: C = H_main(Lx) -> b0, D = H_off(Ly) -> b1, E = H_off(Lx) -> b2 : cols x0-4.. (72 wide), R2 rows;
+       // the centre float4 of each group is the final Lx / Ly of that position -> global store for tile pixels
+        constexpr int GW = 72 / 4, TOT = GW * G::R2, IT = (TOT + 255) / 256;
         float* ox = oLx + ibase;
         float* oy = oLy + ibase;
-        for (int g = tid; g < GW * G::R2; g += 256) {
-            const int gy = g / GW, gx = g - gy * GW;
-            const int ry = gy + (G::HLY - G::HY2);  // row in b1/b2
-            const float* a = b1 + ry * G::P1 + 4 * gx;
-            const float* b = b2 + ry * G::P1 + 4 * gx;
-            const float4 lx = sub4(ld4(a + S * G::P1), ld4(a - S * G::P1));
-            const float4 ly = vmain(ld4(b - S * G::P1), ld4(b), ld4(b + S * G::P1), n, wn);
-            st4(b3 + gy * G::P1 + 4 * gx, lx);
-            st4(b4 + gy * G::P1 + 4 * gx, ly);
-            const int lxp = 4 * gx - G::HX1, lyp = gy - G::HY2;  // tile-local position of the group
-            if (lxp >= 0 && lxp < 64 && lyp >= 0 && lyp < 32) {
+#pragma unroll
+        for (int it = 0; it < IT; it++) {
+            const int g = tid + 256 * it;
+            if (g < TOT) {
+                const int gy = g / GW, gx = g - gy * GW;
+                const int lxp = 4 * gx - 4, lyp = gy - G::HY2;  // tile-local position of the group
+                const bool in_tile = lxp >= 0 && lxp < 64 && lyp >= 0 && lyp < 32;
                 const size_t o = (size_t)(y0 + lyp) * W + x0 + lxp;
-                st4(ox + o, lx);
-                st4(oy + o, ly);
+                float v[12];
+                load12(b3 + gy * G::P1, G::HX1 - 4 + 4 * gx, v);
+                st4(b0 + gy * G::P0 + 4 * gx, hmain<S>(v, n, wn));
+                st4(b2 + gy * G::P1 + 4 * gx, hoff<S>(v));
+                if (in_tile) st4(ox + o, make_float4(v[4], v[5], v[6], v[7]));
+                load12(b4 + gy * G::P1, G::HX1 - 4 + 4 * gx, v);
+                st4(b1 + gy * G::P1 + 4 * gx, hoff<S>(v));
+                if (in_tile) st4(oy + o, make_float4(v[4], v[5], v[6], v[7]));
             }
         }
     }
     __syncthreads();
-    {  // stage 3: C = H_main(Lx) -> b0, D = H_off(Ly) -> b1, E = H_off(Lx) -> b2 : cols x0-4.. (72 wide), R2 rows
-        constexpr int GW = 72 / 4;
-        for (int g = tid; g < GW * G::R2; g += 256) {
-            const int gy = g / GW, gx = g - gy * GW;
-            float v[12];
-            load12(b3 + gy * G::P1, G::HX1 - 4 + 4 * gx, v);
-            st4(b0 + gy * G::P0 + 4 * gx, hmain<S>(v, n, wn));
-            st4(b2 + gy * G::P1 + 4 * gx, hoff<S>(v));
-            load12(b4 + gy * G::P1, G::HX1 - 4 + 4 * gx, v);
-            st4(b1 + gy * G::P1 + 4 * gx, hoff<S>(v));
-        }
+    if (border) {
+        fix_border(b0, G::P0, x0 - 4, y0 - G::HY2, 72, G::R2, W, H, S, tid, 256);
+        fix_border(b1, G::P1, x0 - 4, y0 - G::HY2, 72, G::R2, W, H, S, tid, 256);
+        fix_border(b2, G::P1, x0 - 4, y0 - G::HY2, 72, G::R2, W, H, S, tid, 256);
     }
-    __syncthreads();
     {  // stage 4: Ldet over cols x0-4.. (72 wide), rows y0-1.. (34 rows) -> b3
-        constexpr int GW = 72 / 4;
-        float* od = oLdet + ibase;
-        for (int g = tid; g < GW * 34; g += 256) {
-            const int gy = g / GW, gx = g - gy * GW;
-            const int ry = gy + (G::HY2 - 1);  // row in b0/b1/b2 (stage-3 rows)
-            const float* c = b0 + ry * G::P0 + 4 * gx;
-            const float* d = b1 + ry * G::P1 + 4 * gx;
-            const float* e = b2 + ry * G::P1 + 4 * gx;
-            const float4 lxx = sub4(ld4(c + S * G::P0), ld4(c - S * G::P0));
-            const float4 lyy = vmain(ld4(d - S * G::P1), ld4(d), ld4(d + S * G::P1), n, wn);
-            const float4 lxy = vmain(ld4(e - S * G::P1), ld4(e), ld4(e + S * G::P1), n, wn);
-            float4 det;  // detector_response.rs:52
-            det.x = ((lxx.x * lyy.x) - (lxy.x * lxy.x)) * p.quat;
-            det.y = ((lxx.y * lyy.y) - (lxy.y * lxy.y)) * p.quat;
-            det.z = ((lxx.z * lyy.z) - (lxy.z * lxy.z)) * p.quat;
-            det.w = ((lxx.w * lyy.w) - (lxy.w * lxy.w)) * p.quat;
-            st4(b3 + gy * G::P1 + 4 * gx, det);
-            const int lxp = 4 * gx - 4, lyp = gy - 1;
-            if (lxp >= 0 && lxp < 64 && lyp >= 0 && lyp < 32) {
-                const size_t o = (size_t)(y0 + lyp) * W + x0 + lxp;
-                st4(od + o, det);
-                if (oLxx != nullptr) {
-                    st4(oLxx + ibase + o, lxx);
-                    st4(oLyy + ibase + o, lyy);
-                    st4(oLxy + ibase + o, lxy);
-                }
+        constexpr int GW = 72 / 4, TOT = GW * 34, IT = (TOT + 255) / 256;
+#pragma unroll
+        for (int it = 0; it < IT; it++) {
+            const int g = tid + 256 * it;
+            if (g < TOT) {
+                const int gy = g / GW, gx = g - gy * GW;
+                const int ry = gy + (G::HY2 - 1);  // row in b0/b1/b2 (stage-3 rows)
+                const float* c = b0 + ry * G::P0 + 4 * gx;
+                const float* d = b1 + ry * G::P1 + 4 * gx;
+                const float* e = b2 + ry * G::P1 + 4 * gx;
+                const float4 lxx = sub4(ld4(c + S * G::P0), ld4(c - S * G::P0));
+                const float4 lyy = vmain(ld4(d - S * G::P1), ld4(d), ld4(d + S * G::P1), n, wn);
+                const float4 lxy = vmain(ld4(e - S * G::P1), ld4(e), ld4(e + S * G::P1), n, wn);
+                float4 det;  // detector_response.rs:52
+                det.x = ((lxx.x * lyy.x) - (lxy.x * lxy.x)) * p.quat;
+                det.y = ((lxx.y * lyy.y) - (lxy.y * lxy.y)) * p.quat;
+                det.z = ((lxx.z * lyy.z) - (lxy.z * lxy.z)) * p.quat;
+                det.w = ((lxx.w * lyy.w) - (lxy.w * lxy.w)) * p.quat;
+                st4(b3 + gy * G::P1 + 4 * gx, det);
             }
         }
     }
     __syncthreads();
-    {  // stage 5: threshold + strict 4-neighbour maximum + is_out; b3 holds Ldet at (col lx+4, row ly+1)
+    // Lxx/Lyy/Lxy are clamp-replicated like every pass output, and so is their pointwise product
+    if (border) fix_border(b3, G::P1, x0 - 4, y0 - 1, 72, 34, W, H, S, tid, 256);
+    {  // stage 5: Ldet store + threshold + strict 4-neighbour maximum + is_out; b3 holds Ldet at (col lx+4, row ly+1)
         unsigned int* m = mask + (size_t)img * mask_img_words;
+        float* od = oLdet + ibase;
         const int lane = tid & 31, wid = tid >> 5;
-        for (int ly = wid; ly < 32; ly += 8) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int ly = wid + 8 * k;
             const int y = y0 + ly;
 #pragma unroll
             for (int hx = 0; hx < 2; hx++) {
                 const int lx = lane + 32 * hx, x = x0 + lx;
+                const float* q = b3 + (ly + 1) * G::P1 + lx + 4;
+                const float v = q[0];
+                od[(size_t)y * W + x] = v;
                 bool cand = false;
-                if (x >= p.xmin && x <= p.xmax && y >= p.ymin && y <= p.ymax) {
-                    const float* q = b3 + (ly + 1) * G::P1 + lx + 4;
-                    const float v = q[0];
+                if (x >= p.xmin && x <= p.xmax && y >= p.ymin && y <= p.ymax)
                     cand = v > p.thr && v > q[1] && v > q[-1] && v > q[-G::P1] && v > q[G::P1];
-                }
                 const unsigned int bal = __ballot_sync(0xffffffffu, cand);
-                if (bal != 0 && lane == 0) atomicOr(&m[(size_t)y * p.wpr + (x0 >> 5) + hx], bal);
+                if (bal != 0 && lane == 0) {
+                    const int xs = x0 + 32 * hx, w0 = xs >> 5, sh = xs & 31;
+                    atomicOr(&m[(size_t)y * p.wpr + w0], bal << sh);
+                    if (sh != 0 && (bal >> (32 - sh)) != 0) atomicOr(&m[(size_t)y * p.wpr + w0 + 1], bal >> (32 - sh));
+                }
             }
         }
     }
@@ -488,33 +503,33 @@ int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level)
     p.ymax = lv.ymax;
     p.wpr = lv.wpr;
     const size_t img_px = (size_t)lv.w * lv.h;
-    // float4 fast path for interior tiles: rows and image slabs must be 16-byte aligned
-    p.fast = (lv.w % 4 == 0 && img_px % 4 == 0 && lv.s_det >= 2 && lv.s_det <= 4 && lv.w >= 64 + 2 * (4 * lv.s_det + 4) &&
-              lv.h >= 32 + 2 * (4 * lv.s_det + 4)) ? 1 : 0;
-    const int HL = 2 * lv.s_det + 1, PW = DT + 2 * HL;
-    const size_t smem = (size_t)5 * PW * PW * sizeof(float);
+    // float4 kernel: rows and image slabs 16-byte aligned, compile-time Scharr scale; otherwise (odd widths,
+    // unusual scales, or keep-evolutions mode that also wants Lxx/Lyy/Lxy) the generic kernel
+    const bool fast = lv.w % 4 == 0 && img_px % 4 == 0 && lv.s_det >= 2 && lv.s_det <= 4 && !B.keep;
+    p.fast = fast ? 1 : 0;
     const size_t off = (size_t)lv.off * L.batch;
     // level 0: Lsmooth is Lt (lib.rs:58)
     const float* ls = (level == 0) ? B.Lt : (B.keep ? B.Lsmooth + off : B.Lsmooth);
+    unsigned int* mk = B.mask + lv.mask_off;
+    if (fast) {
+        dim3 gf((lv.w + 63) / 64, (lv.h + 31) / 32, L.batch);
+        if (lv.s_det == 2)
+            k_detector_fast<2><<<gf, 256, DetGeo<2>::FLOATS * sizeof(float), L.stream>>>(ls, img_px, B.Lx + off, B.Ly + off, B.Ldet + off, mk, (size_t)P.dev.mask_words, p);
+        else if (lv.s_det == 3)
+            k_detector_fast<3><<<gf, 256, DetGeo<3>::FLOATS * sizeof(float), L.stream>>>(ls, img_px, B.Lx + off, B.Ly + off, B.Ldet + off, mk, (size_t)P.dev.mask_words, p);
+        else
+            k_detector_fast<4><<<gf, 256, DetGeo<4>::FLOATS * sizeof(float), L.stream>>>(ls, img_px, B.Lx + off, B.Ly + off, B.Ldet + off, mk, (size_t)P.dev.mask_words, p);
+        return 1;
+    }
+    const int HL = 2 * lv.s_det + 1, PW = DT + 2 * HL;
+    const size_t smem = (size_t)5 * PW * PW * sizeof(float);
     float* xx = B.keep ? B.Lxx + off : nullptr;
     float* yy = B.keep ? B.Lyy + off : nullptr;
     float* xy = B.keep ? B.Lxy + off : nullptr;
-    unsigned int* mk = B.mask + lv.mask_off;
-    int launches = 0;
-    if (p.fast) {
-        dim3 gf(lv.w / 64, lv.h / 32, L.batch);
-        if (lv.s_det == 2)
-            k_detector_fast<2><<<gf, 256, DetGeo<2>::FLOATS * sizeof(float), L.stream>>>(ls, img_px, B.Lx + off, B.Ly + off, B.Ldet + off, xx, yy, xy, mk, (size_t)P.dev.mask_words, p);
-        else if (lv.s_det == 3)
-            k_detector_fast<3><<<gf, 256, DetGeo<3>::FLOATS * sizeof(float), L.stream>>>(ls, img_px, B.Lx + off, B.Ly + off, B.Ldet + off, xx, yy, xy, mk, (size_t)P.dev.mask_words, p);
-        else
-            k_detector_fast<4><<<gf, 256, DetGeo<4>::FLOATS * sizeof(float), L.stream>>>(ls, img_px, B.Lx + off, B.Ly + off, B.Ldet + off, xx, yy, xy, mk, (size_t)P.dev.mask_words, p);
-        launches++;
-    }
     dim3 grid((lv.w + DT - 1) / DT, (lv.h + DT - 1) / DT, L.batch);
     k_detector<<<grid, dim3(NTX, NTY), smem, L.stream>>>(ls, img_px, B.Lx + off, B.Ly + off, B.Ldet + off, xx, yy, xy, mk,
                                                          (size_t)P.dev.mask_words, p);
-    return launches + 1;
+    return 1;
 }
 
 int launch_compact(const Launch& L, const Plan& P, const Buffers& B) {

@@ -1,0 +1,71 @@
+// tile_util.cuh -- helpers shared by the float4 ("fast") tile kernels.
+//
+// Fast tile kernels keep every shared-memory stage buffer in rows whose x extent is a multiple of 4 and
+// whose origin is 16-byte aligned, so that each thread produces 4 horizontally adjacent outputs from
+// aligned float4 loads. They need W % 4 == 0 and 16-byte aligned image slabs; other shapes use the
+// generic scalar kernels. Border semantics (fill_border, akaze/src/types/image.rs:239-260) are applied
+// after each pass by fix_border below, only in blocks whose regions touch a clamp band.
+#pragma once
+
+#include <cuda_runtime.h>
+
+namespace akz {
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 sub4(const float4& a, const float4& b) {
+    return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
+}
+
+// v[0..11] = row[cx-4 .. cx+7] (cx a multiple of 4)
+__device__ __forceinline__ void load12(const float* row, int cx, float (&v)[12]) {
+    const float4 a = ld4(row + cx - 4), b = ld4(row + cx), c = ld4(row + cx + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    v[8] = c.x; v[9] = c.y; v[10] = c.z; v[11] = c.w;
+}
+
+// 3-tap vertical pass on float4 rows: (k0*a + k1*b) + k2*c per component, in tap order
+__device__ __forceinline__ float4 vtap3(const float4& a, const float4& b, const float4& c, float k0, float k1, float k2) {
+    return make_float4((k0 * a.x + k1 * b.x) + k2 * c.x, (k0 * a.y + k1 * b.y) + k2 * c.y, (k0 * a.z + k1 * b.z) + k2 * c.z,
+                       (k0 * a.w + k1 * b.w) + k2 * c.w);
+}
+
+// fill_border of one filter pass applied to a shared-memory stage buffer (image.rs:239-260 in closed
+// form): positions of the region whose coordinate is inside the hw-wide clamp band of the IMAGE take
+// the value at the clamped coordinate -- rows first, then columns, like the reference. The region is
+// [rx0, rx0+rw) x [ry0, ry0+rh) in image coordinates, stored with pitch P from buf. Called by every
+// thread of a block whose region touches a clamp band (block-uniform); contains two barriers.
+__device__ __forceinline__ void fix_border(float* buf, int P, int rx0, int ry0, int rw, int rh, int W, int H, int hw, int tid,
+                                           int nthreads) {
+    const int xa = max(rx0, 0), xb = min(rx0 + rw, W);
+    const int ya = max(ry0, 0), yb = min(ry0 + rh, H);
+    {   // rows above hw copy row hw, rows below H-1-hw copy row H-1-hw
+        const int ntop = max(0, min(hw, yb) - ya);
+        const int bot0 = max(H - hw, ya);
+        const int nbot = max(0, yb - bot0);
+        const int wv = xb - xa;
+        for (int i = tid; i < (ntop + nbot) * wv; i += nthreads) {
+            const int r = i / wv, x = xa + (i - r * wv);
+            const int y = r < ntop ? ya + r : bot0 + (r - ntop);
+            const int sy = r < ntop ? hw : H - 1 - hw;
+            buf[(y - ry0) * P + (x - rx0)] = buf[(sy - ry0) * P + (x - rx0)];
+        }
+    }
+    __syncthreads();
+    {   // columns left of hw copy column hw, right of W-1-hw copy column W-1-hw
+        const int nl = max(0, min(hw, xb) - xa);
+        const int r0 = max(W - hw, xa);
+        const int nr = max(0, xb - r0);
+        const int hv = yb - ya;
+        for (int i = tid; i < (nl + nr) * hv; i += nthreads) {
+            const int c = i / hv, y = ya + (i - c * hv);
+            const int x = c < nl ? xa + c : r0 + (c - nl);
+            const int sx = c < nl ? hw : W - 1 - hw;
+            buf[(y - ry0) * P + (x - rx0)] = buf[(y - ry0) * P + (sx - rx0)];
+        }
+    }
+    __syncthreads();
+}
+
+}  // namespace akz
