@@ -112,6 +112,7 @@ std::string build_plan(uint32_t w, uint32_t h, const akz_config& cfg, Plan* P) {
         const int s0 = (int)ceilf(pf * 1.0f), s1 = (int)ceilf(pf * (2.0f / 3.0f)), s2 = (int)ceilf(pf * (1.0f / 2.0f));
         const int n0 = (2 * p + s0 - 1) / s0, n1 = (2 * p + s1 - 1) / s1, n2 = (2 * p + s2 - 1) / s2;
         if (n0 != 2 || n1 != 3 || n2 != 4) return "descriptor_pattern_size does not give the 2x2/3x3/4x4 MLDB grids";
+        if (4 * s0 * s0 > 448 || 9 * s1 * s1 > 448 || 16 * s2 * s2 > 448) return "descriptor_pattern_size too large (max 10)";
     }
     P->w = w;
     P->h = h;
@@ -266,18 +267,51 @@ std::string build_plan(uint32_t w, uint32_t h, const akz_config& cfg, Plan* P) {
 using namespace akz;
 
 // ---- context -----------------------------------------------------------------------------------
+// One extraction call is cut into sub-batches that flow through a two-stage software pipeline:
+//   stage A (stream `stream`):    upload-independent stencil work -- level 0, contrast, per level
+//                                 prep / FED / detector, candidate compaction;
+//   stage B (stream `stream_kp`): the latency-bound keypoint stages -- cache pass, filter/refine,
+//                                 orientation, descriptors.
+// Two "lanes" of work buffers alternate between consecutive sub-batches, so stage B of sub-batch i
+// overlaps stage A of sub-batch i+1. Results of all images of the call live in context-level arrays.
+struct Lane {
+    Buffers buf;
+    std::vector<void*> allocs;
+    int alloc_batch = 0;
+    cudaEvent_t ev_stencil = nullptr;  // stage A of the sub-batch using this lane has finished
+    cudaEvent_t ev_done = nullptr;     // stage B of the sub-batch using this lane has finished
+    bool busy = false;
+};
+
+struct Results {
+    akz_keypoint* kps = nullptr;        // [n][kp_cap]
+    uint8_t* desc = nullptr;            // [n][kp_cap][64]
+    unsigned int* n_kp = nullptr;       // [n]
+    unsigned int* n_cache = nullptr;
+    unsigned int* n_cand = nullptr;
+    unsigned int* err = nullptr;
+    double* kcontrast = nullptr;        // [n][kMaxLevels]
+    uint8_t* in_u8 = nullptr;           // staging for host inputs, [n][h][w]
+    float* in_f32 = nullptr;
+    std::vector<void*> allocs;
+    int alloc_n = 0;
+};
+
 struct akz_context {
     int device = 0;
     uint32_t max_w = 0, max_h = 0, max_batch = 0, flags = 0;
     uint32_t cand_cap = 262144, kp_cap = 65536;
-    cudaStream_t stream = nullptr;
+    uint32_t sub_batch = 64;           // images per pipeline sub-batch
+    cudaStream_t stream = nullptr;     // stage A, copies, and the stream callers may time on
+    cudaStream_t stream_kp = nullptr;  // stage B
+    cudaStream_t stream_copy = nullptr;  // host -> device staging of the inputs, one event per sub-batch
+    std::vector<cudaEvent_t> ev_copy;
     uint64_t launches = 0;
     uint64_t generation = 0;
     bool have_plan = false;
     Plan plan;
-    Buffers buf;
-    int alloc_batch = 0;           // batch the buffers are sized for
-    std::vector<void*> allocs;     // everything in buf
+    Lane lane[2];
+    Results res;
     int cur_batch = 0;
     // per-stage timing
     bool timing = false;
@@ -307,80 +341,112 @@ struct akz_features {
     uint64_t n_cand = 0, n_cache = 0;
 };
 
+static void free_lane(Lane& ln) {
+    for (void* p : ln.allocs) cudaFree(p);
+    ln.allocs.clear();
+    ln.buf = Buffers();
+    ln.alloc_batch = 0;
+    ln.busy = false;
+}
+static void free_results(Results& r) {
+    for (void* p : r.allocs) cudaFree(p);
+    r = Results();
+}
 static void free_buffers(akz_context* c) {
-    for (void* p : c->allocs) cudaFree(p);
-    c->allocs.clear();
-    c->buf = Buffers();
-    c->alloc_batch = 0;
+    free_lane(c->lane[0]);
+    free_lane(c->lane[1]);
+    free_results(c->res);
 }
 
 template <class T>
-static cudaError_t dalloc(akz_context* c, T** p, size_t count) {
+static cudaError_t dalloc(std::vector<void*>& owner, T** p, size_t count) {
     void* v = nullptr;
     cudaError_t e = cudaMalloc(&v, std::max<size_t>(count, 1) * sizeof(T));
     if (e != cudaSuccess) return e;
-    c->allocs.push_back(v);
+    owner.push_back(v);
     *p = (T*)v;
     return cudaSuccess;
 }
 
-static int ensure_buffers(akz_context* c, int batch, bool plan_changed) {
-    if (!plan_changed && batch <= c->alloc_batch) return AKZ_OK;
-    free_buffers(c);
+static int ensure_lane(akz_context* c, Lane& ln, int batch) {
+    if (batch <= ln.alloc_batch) return AKZ_OK;
+    free_lane(ln);
     const Plan& P = c->plan;
-    Buffers& B = c->buf;
+    Buffers& B = ln.buf;
+    std::vector<void*>& A = ln.allocs;
     const size_t nb = (size_t)batch;
     const size_t plane = (size_t)P.dev.plane_px * nb;
     const size_t n0 = (size_t)P.w * P.h * nb;
     B.keep = (c->flags & AKZ_KEEP_EVOLUTIONS) != 0;
-    CK(dalloc(c, &B.Lt, plane));
-    CK(dalloc(c, &B.Lx, plane));
-    CK(dalloc(c, &B.Ly, plane));
-    CK(dalloc(c, &B.Ldet, plane));
-    CK(dalloc(c, &B.Lsmooth, B.keep ? plane : n0));
-    CK(dalloc(c, &B.Lflow, B.keep ? plane : n0));
-    CK(dalloc(c, &B.Ltmp, n0));
+    CK(dalloc(A, &B.Lt, plane));
+    CK(dalloc(A, &B.Lx, plane));
+    CK(dalloc(A, &B.Ly, plane));
+    CK(dalloc(A, &B.Ldet, plane));
+    CK(dalloc(A, &B.Lsmooth, B.keep ? plane : n0));
+    CK(dalloc(A, &B.Lflow, B.keep ? plane : n0));
+    CK(dalloc(A, &B.Ltmp, n0));
     if (B.keep) {
-        CK(dalloc(c, &B.Lxx, plane));
-        CK(dalloc(c, &B.Lyy, plane));
-        CK(dalloc(c, &B.Lxy, plane));
-        CK(dalloc(c, &B.Lstep, plane));
+        CK(dalloc(A, &B.Lxx, plane));
+        CK(dalloc(A, &B.Lyy, plane));
+        CK(dalloc(A, &B.Lxy, plane));
+        CK(dalloc(A, &B.Lstep, plane));
         CK(cudaMemset(B.Lstep, 0, plane * sizeof(float)));
     }
-    CK(dalloc(c, &B.in_u8, n0));
-    CK(dalloc(c, &B.in_f32, n0));
-    CK(dalloc(c, &B.hmax_bits, nb));
-    CK(dalloc(c, &B.hist, nb * kMaxBins));
-    CK(dalloc(c, &B.kcontrast, nb * kMaxLevels));
-    CK(dalloc(c, &B.mask, (size_t)P.dev.mask_words * nb));
-    CK(dalloc(c, &B.cand, (size_t)c->cand_cap * nb));
+    CK(dalloc(A, &B.hmax_bits, nb));
+    CK(dalloc(A, &B.hist, nb * kMaxBins));
+    CK(dalloc(A, &B.mask, (size_t)P.dev.mask_words * nb));
+    CK(dalloc(A, &B.cand, (size_t)c->cand_cap * nb));
     size_t total_rows = 0;
     for (int l = 0; l < P.dev.n_levels; l++) total_rows += P.dev.lv[l].h;
-    CK(dalloc(c, &B.rowcount, total_rows * nb));
-    CK(dalloc(c, &B.cand_level_count, nb * (kMaxLevels + 1)));
+    CK(dalloc(A, &B.rowcount, total_rows * nb));
+    CK(dalloc(A, &B.cand_level_count, nb * (kMaxLevels + 1)));
     const size_t kc = (size_t)c->kp_cap * nb;
-    CK(dalloc(c, &B.c_x, kc));
-    CK(dalloc(c, &B.c_y, kc));
-    CK(dalloc(c, &B.c_resp, kc));
-    CK(dalloc(c, &B.r_x, kc));
-    CK(dalloc(c, &B.r_y, kc));
-    CK(dalloc(c, &B.c_cls, kc));
-    CK(dalloc(c, &B.c_next, kc));
-    CK(dalloc(c, &B.grid, nb * 2 * (size_t)P.dev.grid_w * P.dev.grid_h));
-    CK(dalloc(c, &B.n_cache, nb));
-    CK(dalloc(c, &B.n_cand_total, nb));
-    CK(dalloc(c, &B.keep_flag, kc));
-    CK(dalloc(c, &B.n_kp, nb));
-    CK(dalloc(c, &B.err_flags, nb));
-    CK(dalloc(c, &B.kps, kc));
-    CK(dalloc(c, &B.desc, kc * kDescStride));
-    CK(dalloc(c, &B.plan_dev, 1));
+    CK(dalloc(A, &B.c_x, kc));
+    CK(dalloc(A, &B.c_y, kc));
+    CK(dalloc(A, &B.c_resp, kc));
+    CK(dalloc(A, &B.r_x, kc));
+    CK(dalloc(A, &B.r_y, kc));
+    CK(dalloc(A, &B.c_cls, kc));
+    CK(dalloc(A, &B.c_next, kc));
+    CK(dalloc(A, &B.grid, nb * 2 * (size_t)P.dev.grid_w * P.dev.grid_h));
+    CK(dalloc(A, &B.keep_flag, kc));
+    CK(dalloc(A, &B.cls_range, nb * kMaxLevels * 2));
+    CK(dalloc(A, &B.plan_dev, 1));
     CK(cudaMemcpy(B.plan_dev, &P.dev, sizeof(PlanDev), cudaMemcpyHostToDevice));
-    c->alloc_batch = batch;
+    if (!ln.ev_stencil) {
+        CK(cudaEventCreateWithFlags(&ln.ev_stencil, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ln.ev_done, cudaEventDisableTiming));
+    }
+    ln.alloc_batch = batch;
+    return AKZ_OK;
+}
+
+static int ensure_results(akz_context* c, int n) {
+    Results& R = c->res;
+    if (n <= R.alloc_n) return AKZ_OK;
+    free_results(R);
+    const size_t nb = (size_t)n, kc = (size_t)c->kp_cap * nb;
+    const size_t n0 = (size_t)c->plan.w * c->plan.h * nb;
+    CK(dalloc(R.allocs, &R.kps, kc));
+    CK(dalloc(R.allocs, &R.desc, kc * kDescStride));
+    CK(dalloc(R.allocs, &R.n_kp, nb));
+    CK(dalloc(R.allocs, &R.n_cache, nb));
+    CK(dalloc(R.allocs, &R.n_cand, nb));
+    CK(dalloc(R.allocs, &R.err, nb));
+    CK(dalloc(R.allocs, &R.kcontrast, nb * kMaxLevels));
+    CK(dalloc(R.allocs, &R.in_u8, n0));
+    CK(dalloc(R.allocs, &R.in_f32, (size_t)c->plan.w * c->plan.h));  // akz_extract_f32 is single-image
+    R.alloc_n = n;
     return AKZ_OK;
 }
 
 static bool same_cfg(const akz_config& a, const akz_config& b) { return memcmp(&a, &b, sizeof(akz_config)) == 0; }
+
+// images per sub-batch for a call of n images
+static uint32_t sub_batch_of(const akz_context* c, uint32_t n) {
+    if (c->flags & AKZ_KEEP_EVOLUTIONS) return n;  // evolutions of every image of the call stay resident
+    return std::min(n, c->sub_batch);
+}
 
 static int prepare(akz_context* c, uint32_t n, uint32_t w, uint32_t h, const akz_config* cfg) {
     if (!c || !cfg) return fail(AKZ_ERR_INVALID, "null argument");
@@ -388,7 +454,6 @@ static int prepare(akz_context* c, uint32_t n, uint32_t w, uint32_t h, const akz
     if (n > c->max_batch) return fail(AKZ_ERR_CAPACITY, "batch larger than the context's max_batch");
     if (w > c->max_w || h > c->max_h) return fail(AKZ_ERR_CAPACITY, "image larger than the context's max size");
     CK(cudaSetDevice(c->device));
-    bool changed = false;
     if (!c->have_plan || c->plan.w != w || c->plan.h != h || !same_cfg(c->plan.cfg, *cfg)) {
         akz_config z;
         memset(&z, 0, sizeof(z));  // normalise struct padding before memcmp-style comparison
@@ -405,19 +470,28 @@ static int prepare(akz_context* c, uint32_t n, uint32_t w, uint32_t h, const akz
         Plan np;
         std::string err = build_plan(w, h, z, &np);
         if (!err.empty()) return fail(AKZ_ERR_INVALID, err);
+        CK(cudaStreamSynchronize(c->stream));
+        CK(cudaStreamSynchronize(c->stream_kp));
+        free_buffers(c);
         c->plan = np;
         c->have_plan = true;
-        changed = true;
     }
-    return ensure_buffers(c, (int)n, changed);
+    const uint32_t m = sub_batch_of(c, n);
+    int rc = ensure_lane(c, c->lane[0], (int)m);
+    if (rc != AKZ_OK) return rc;
+    if (n > m) {
+        rc = ensure_lane(c, c->lane[1], (int)m);
+        if (rc != AKZ_OK) return rc;
+    }
+    return ensure_results(c, (int)n);
 }
 
 // brackets one stage's launches with events when timing is on
 struct StageTimer {
     akz_context* c;
-    int stage;
+    cudaStream_t st;
     size_t slot = (size_t)-1;
-    StageTimer(akz_context* ctx, int st) : c(ctx), stage(st) {
+    StageTimer(akz_context* ctx, int stage, cudaStream_t stream) : c(ctx), st(stream) {
         if (!c->timing) return;
         if (c->ev_used == c->ev_pool.size()) {
             cudaEvent_t a, b;
@@ -429,16 +503,16 @@ struct StageTimer {
         }
         slot = c->ev_used++;
         c->ev_stage[slot] = stage;
-        cudaEventRecord(c->ev_pool[slot].first, c->stream);
+        cudaEventRecord(c->ev_pool[slot].first, st);
     }
     void done(int launches) {
         if (slot == (size_t)-1) return;
         c->ev_launches[slot] = launches;
-        cudaEventRecord(c->ev_pool[slot].second, c->stream);
+        cudaEventRecord(c->ev_pool[slot].second, st);
     }
 };
 
-// folds finished event pairs into the per-stage totals (stream must be idle)
+// folds finished event pairs into the per-stage totals (streams must be idle)
 static void harvest_timing(akz_context* c) {
     for (size_t i = 0; i < c->ev_used; i++) {
         float ms = 0.0f;
@@ -450,36 +524,64 @@ static void harvest_timing(akz_context* c) {
     c->ev_used = 0;
 }
 
-// runs the whole pipeline on inputs already in device memory; results stay on the device
-static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8, size_t in_stride) {
+// runs the whole pipeline on inputs already in device memory; results stay on the device (c->res).
+// On return everything has been ISSUED and c->stream waits for all of it.
+static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8, size_t in_stride, bool wait_copies = false) {
     const Plan& P = c->plan;
-    const Buffers& B = c->buf;
-    Launch L{c->stream, (int)n, c->cand_cap, c->kp_cap};
+    const Results& R = c->res;
+    const uint32_t m = sub_batch_of(c, n);
     c->generation++;
     c->cur_batch = (int)n;
-    CK(cudaMemsetAsync(B.mask, 0, (size_t)P.dev.mask_words * n * sizeof(unsigned int), c->stream));
-    CK(cudaMemsetAsync(B.err_flags, 0, n * sizeof(unsigned int), c->stream));
+    const size_t in_img = in_stride * P.h * (is_u8 ? 1 : sizeof(float));  // bytes per input image
     int k = 0, j;
-#define STAGE(st, expr)          \
-    {                            \
-        StageTimer t__(c, st);   \
-        j = (expr);              \
-        t__.done(j);             \
-        k += j;                  \
+#define STAGE(st, strm, expr)          \
+    {                                  \
+        StageTimer t__(c, st, strm);   \
+        j = (expr);                    \
+        t__.done(j);                   \
+        k += j;                        \
     }
-    STAGE(AKZ_STAGE_LEVEL0, launch_level0(L, P, B, d_in, is_u8, in_stride));
-    STAGE(AKZ_STAGE_CONTRAST, launch_contrast(L, P, B));
-    STAGE(AKZ_STAGE_DETECTOR, launch_detector(L, P, B, 0));
-    for (int l = 1; l < P.dev.n_levels; l++) {
-        STAGE(AKZ_STAGE_PREP, launch_prep(L, P, B, l));
-        STAGE(AKZ_STAGE_FED, launch_fed(L, P, B, l));
-        STAGE(AKZ_STAGE_DETECTOR, launch_detector(L, P, B, l));
+    for (uint32_t i0 = 0, sb = 0; i0 < n; i0 += m, sb++) {
+        Lane& ln = c->lane[sb & 1];
+        const uint32_t cnt = std::min(m, n - i0);
+        if (ln.busy) CK(cudaStreamWaitEvent(c->stream, ln.ev_done, 0));  // the lane's previous sub-batch must be through stage B
+        if (wait_copies) CK(cudaStreamWaitEvent(c->stream, c->ev_copy[sb], 0));  // its inputs must have arrived
+        Buffers B = ln.buf;
+        B.kps = R.kps + (size_t)i0 * c->kp_cap;
+        B.desc = R.desc + (size_t)i0 * c->kp_cap * kDescStride;
+        B.n_kp = R.n_kp + i0;
+        B.n_cache = R.n_cache + i0;
+        B.n_cand_total = R.n_cand + i0;
+        B.err_flags = R.err + i0;
+        B.kcontrast = R.kcontrast + (size_t)i0 * kMaxLevels;
+        const void* in = (const uint8_t*)d_in + (size_t)i0 * in_img;
+        Launch LA{c->stream, (int)cnt, c->cand_cap, c->kp_cap};
+        CK(cudaMemsetAsync(B.mask, 0, (size_t)P.dev.mask_words * cnt * sizeof(unsigned int), c->stream));
+        CK(cudaMemsetAsync(B.err_flags, 0, cnt * sizeof(unsigned int), c->stream));
+        STAGE(AKZ_STAGE_LEVEL0, c->stream, launch_level0(LA, P, B, in, is_u8, in_stride));
+        STAGE(AKZ_STAGE_CONTRAST, c->stream, launch_contrast(LA, P, B));
+        STAGE(AKZ_STAGE_DETECTOR, c->stream, launch_detector(LA, P, B, 0));
+        for (int l = 1; l < P.dev.n_levels; l++) {
+            STAGE(AKZ_STAGE_PREP, c->stream, launch_prep(LA, P, B, l));
+            STAGE(AKZ_STAGE_FED, c->stream, launch_fed(LA, P, B, l));
+            STAGE(AKZ_STAGE_DETECTOR, c->stream, launch_detector(LA, P, B, l));
+        }
+        STAGE(AKZ_STAGE_COMPACT, c->stream, launch_compact(LA, P, B));
+        CK(cudaEventRecord(ln.ev_stencil, c->stream));
+        CK(cudaStreamWaitEvent(c->stream_kp, ln.ev_stencil, 0));
+        Launch LB{c->stream_kp, (int)cnt, c->cand_cap, c->kp_cap};
+        STAGE(AKZ_STAGE_DEDUP, c->stream_kp, launch_dedup(LB, P, B));
+        STAGE(AKZ_STAGE_FINALIZE, c->stream_kp, launch_finalize(LB, P, B));
+        STAGE(AKZ_STAGE_DESCRIPTOR, c->stream_kp, launch_descriptors(LB, P, B));
+        CK(cudaEventRecord(ln.ev_done, c->stream_kp));
+        ln.busy = true;
     }
-    STAGE(AKZ_STAGE_COMPACT, launch_compact(L, P, B));
-    STAGE(AKZ_STAGE_DEDUP, launch_dedup(L, P, B));
-    STAGE(AKZ_STAGE_FINALIZE, launch_finalize(L, P, B));
-    STAGE(AKZ_STAGE_DESCRIPTOR, launch_descriptors(L, P, B));
 #undef STAGE
+    for (int l = 0; l < 2; l++)
+        if (c->lane[l].busy) {
+            CK(cudaStreamWaitEvent(c->stream, c->lane[l].ev_done, 0));
+            c->lane[l].busy = false;
+        }
     c->launches += (uint64_t)k;
     CK(cudaGetLastError());
     return AKZ_OK;
@@ -491,17 +593,17 @@ struct BatchStats {
 };
 
 static int fetch_stats(akz_context* c, uint32_t n, BatchStats* s) {
-    const Buffers& B = c->buf;
+    const Results& R = c->res;
     s->n_kp.resize(n);
     s->n_cache.resize(n);
     s->n_cand.resize(n);
     s->err.resize(n);
     s->kcontrast.resize((size_t)n * kMaxLevels);
-    CK(cudaMemcpyAsync(s->n_kp.data(), B.n_kp, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(s->n_cache.data(), B.n_cache, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(s->n_cand.data(), B.n_cand_total, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(s->err.data(), B.err_flags, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(s->kcontrast.data(), B.kcontrast, (size_t)n * kMaxLevels * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(s->n_kp.data(), R.n_kp, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(s->n_cache.data(), R.n_cache, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(s->n_cand.data(), R.n_cand, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(s->err.data(), R.err, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(s->kcontrast.data(), R.kcontrast, (size_t)n * kMaxLevels * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
     if (c->timing) harvest_timing(c);
     for (uint32_t i = 0; i < n; i++) {
@@ -516,7 +618,7 @@ static int collect_features(akz_context* c, uint32_t n, akz_features** outs) {
     BatchStats st;
     int rc = fetch_stats(c, n, &st);
     if (rc != AKZ_OK) return rc;
-    const Buffers& B = c->buf;
+    const Results& R = c->res;
     std::vector<std::unique_ptr<akz_features>> fs;
     for (uint32_t i = 0; i < n; i++) {
         std::unique_ptr<akz_features> f(new akz_features());
@@ -533,8 +635,8 @@ static int collect_features(akz_context* c, uint32_t n, akz_features** outs) {
         f->kps.resize(nk);
         f->desc.resize(nk * kDescStride);
         if (nk) {
-            CK(cudaMemcpyAsync(f->kps.data(), B.kps + (size_t)i * c->kp_cap, nk * sizeof(akz_keypoint), cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaMemcpyAsync(f->desc.data(), B.desc + (size_t)i * c->kp_cap * kDescStride, nk * kDescStride, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(f->kps.data(), R.kps + (size_t)i * c->kp_cap, nk * sizeof(akz_keypoint), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(f->desc.data(), R.desc + (size_t)i * c->kp_cap * kDescStride, nk * kDescStride, cudaMemcpyDeviceToHost, c->stream));
         }
         fs.push_back(std::move(f));
     }
@@ -583,6 +685,8 @@ int akz_create(int device, uint32_t max_width, uint32_t max_height, uint32_t max
     c->max_batch = max_batch;
     c->flags = flags;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->stream_kp, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking));
     CK(init_detector_attributes());
     CK(init_keypoint_attributes());
     *out = c.release();
@@ -593,7 +697,15 @@ void akz_destroy(akz_context* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->stream_kp);
     free_buffers(c);
+    for (int l = 0; l < 2; l++) {
+        if (c->lane[l].ev_stencil) cudaEventDestroy(c->lane[l].ev_stencil);
+        if (c->lane[l].ev_done) cudaEventDestroy(c->lane[l].ev_done);
+    }
+    cudaStreamDestroy(c->stream_kp);
+    for (cudaEvent_t e : c->ev_copy) cudaEventDestroy(e);
+    cudaStreamDestroy(c->stream_copy);
     cudaFree(c->m_q);
     cudaFree(c->m_db);
     cudaFree(c->m_parts);
@@ -635,6 +747,8 @@ int akz_context_set_limits(akz_context* c, uint32_t max_candidates, uint32_t max
     c->cand_cap = max_candidates;
     c->kp_cap = max_keypoints;
     cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->stream_kp);
     free_buffers(c);
     return AKZ_OK;
 }
@@ -645,11 +759,22 @@ int akz_extract_batch_u8(akz_context* c, uint32_t n, const uint8_t* const* grays
     if (stride < w) return fail(AKZ_ERR_INVALID, "stride < width");
     int rc = prepare(c, n, w, h, cfg);
     if (rc != AKZ_OK) return rc;
-    for (uint32_t i = 0; i < n; i++) {
-        if (!grays[i]) return fail(AKZ_ERR_INVALID, "null image");
-        CK(cudaMemcpy2DAsync(c->buf.in_u8 + (size_t)i * w * h, w, grays[i], stride, w, h, cudaMemcpyHostToDevice, c->stream));
+    // uploads run on their own stream, one event per pipeline sub-batch, so that the copy of sub-batch i+1
+    // overlaps the kernels of sub-batch i (asynchronous when the caller's images are in pinned memory)
+    const uint32_t m = sub_batch_of(c, n);
+    for (uint32_t i0 = 0, sb = 0; i0 < n; i0 += m, sb++) {
+        for (uint32_t i = i0; i < std::min(n, i0 + m); i++) {
+            if (!grays[i]) return fail(AKZ_ERR_INVALID, "null image");
+            CK(cudaMemcpy2DAsync(c->res.in_u8 + (size_t)i * w * h, w, grays[i], stride, w, h, cudaMemcpyHostToDevice, c->stream_copy));
+        }
+        if (c->ev_copy.size() <= sb) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->ev_copy.push_back(e);
+        }
+        CK(cudaEventRecord(c->ev_copy[sb], c->stream_copy));
     }
-    rc = run_pipeline(c, n, c->buf.in_u8, true, w);
+    rc = run_pipeline(c, n, c->res.in_u8, true, w, true);
     if (rc != AKZ_OK) return rc;
     return collect_features(c, n, outs);
 }
@@ -664,8 +789,8 @@ int akz_extract_f32(akz_context* c, const float* unit_gray, uint32_t w, uint32_t
     if (!unit_gray || !out) return fail(AKZ_ERR_INVALID, "null argument");
     int rc = prepare(c, 1, w, h, cfg);
     if (rc != AKZ_OK) return rc;
-    CK(cudaMemcpyAsync(c->buf.in_f32, unit_gray, (size_t)w * h * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    rc = run_pipeline(c, 1, c->buf.in_f32, false, w);
+    CK(cudaMemcpyAsync(c->res.in_f32, unit_gray, (size_t)w * h * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    rc = run_pipeline(c, 1, c->res.in_f32, false, w);
     if (rc != AKZ_OK) return rc;
     return collect_features(c, 1, out);
 }
@@ -686,9 +811,9 @@ int akz_extract_batch_u8_device(akz_context* c, uint32_t n, const void* d_grays,
 }
 
 int akz_context_device_results(akz_context* c, void** d_keypoints, void** d_descriptors, uint32_t* kp_capacity) {
-    if (!c || !c->buf.kps) return fail(AKZ_ERR_INVALID, "no extraction has run on this context");
-    if (d_keypoints) *d_keypoints = c->buf.kps;
-    if (d_descriptors) *d_descriptors = c->buf.desc;
+    if (!c || !c->res.kps) return fail(AKZ_ERR_INVALID, "no extraction has run on this context");
+    if (d_keypoints) *d_keypoints = c->res.kps;
+    if (d_descriptors) *d_descriptors = c->res.desc;
     if (kp_capacity) *kp_capacity = c->kp_cap;
     return AKZ_OK;
 }
@@ -719,7 +844,7 @@ int akz_features_evolution_download(const akz_features* f, uint32_t level, int k
     if (!(c->flags & AKZ_KEEP_EVOLUTIONS)) return fail(AKZ_ERR_INVALID, "context was created without AKZ_KEEP_EVOLUTIONS");
     if (c->generation != f->generation) return fail(AKZ_ERR_INVALID, "evolutions were overwritten by a later extraction");
     CK(cudaSetDevice(c->device));
-    const Buffers& B = c->buf;
+    const Buffers& B = c->lane[0].buf;  // keep-evolutions mode runs the whole call as one sub-batch on lane 0
     const float* plane = nullptr;
     switch (kind) {
         case AKZ_LT: plane = B.Lt; break;

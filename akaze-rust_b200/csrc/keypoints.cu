@@ -350,10 +350,36 @@ k_dedup_smem(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ 
 // K5b: upper-scale filter (:111-129) + pseudo sub-pixel offset (:141-178). One warp per cache slot.
 // keep_flag[i] = 1 iff the slot survives; refined point written back into c_x/c_y.
 // ------------------------------------------------------------------------------------------------
+// slot range [lo, hi] occupied by each class_id (slots are handed out in level order, so the keypoints of
+// class c+1 sit in a narrow slot range; only replaced older slots fall outside the bulk)
+__global__ void __launch_bounds__(256)
+k_class_ranges(const int* __restrict__ c_cls, const unsigned int* __restrict__ n_cache, unsigned int kp_cap,
+               unsigned int* __restrict__ cls_range) {
+    __shared__ unsigned int lo[kMaxLevels], hi[kMaxLevels];
+    const int img = blockIdx.x;
+    const unsigned int n = n_cache[img];
+    if (threadIdx.x < kMaxLevels) {
+        lo[threadIdx.x] = 0xffffffffu;
+        hi[threadIdx.x] = 0u;
+    }
+    __syncthreads();
+    for (unsigned int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int c = c_cls[(size_t)img * kp_cap + i];
+        atomicMin(&lo[c], i);
+        atomicMax(&hi[c], i);
+    }
+    __syncthreads();
+    if (threadIdx.x < kMaxLevels) {
+        cls_range[((size_t)img * kMaxLevels + threadIdx.x) * 2 + 0] = lo[threadIdx.x];
+        cls_range[((size_t)img * kMaxLevels + threadIdx.x) * 2 + 1] = hi[threadIdx.x];
+    }
+}
+
 __global__ void k_filter_refine(const PlanDev* __restrict__ plan, const float* __restrict__ ldet_plane, int batch,
                                 unsigned int kp_cap, const float* __restrict__ c_x, const float* __restrict__ c_y,
                                 const int* __restrict__ c_cls, const unsigned int* __restrict__ n_cache,
-                                float* __restrict__ r_x, float* __restrict__ r_y, unsigned int* __restrict__ keep_flag) {
+                                const unsigned int* __restrict__ cls_range, float* __restrict__ r_x, float* __restrict__ r_y,
+                                unsigned int* __restrict__ keep_flag) {
     const int img = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const unsigned int n = n_cache[img];
@@ -365,10 +391,20 @@ __global__ void k_filter_refine(const PlanDev* __restrict__ plan, const float* _
         const float xi = c_x[o + i], yi = c_y[o + i];
         const float size_sq = lv.size_sq;
         bool rep = false;
-        for (unsigned int j0 = i; j0 < n && !rep; j0 += 32) {
+        // :115 scans slots j >= i for class_id + 1; those all lie inside that class's slot range
+        unsigned int jb = i, je = 0;
+        if (cls + 1 < plan->n_levels) {
+            const unsigned int rl = cls_range[((size_t)img * kMaxLevels + cls + 1) * 2 + 0];
+            const unsigned int rh = cls_range[((size_t)img * kMaxLevels + cls + 1) * 2 + 1];
+            if (rl != 0xffffffffu) {
+                jb = max(i, rl);
+                je = min(n, rh + 1);
+            }
+        }
+        for (unsigned int j0 = jb; j0 < je && !rep; j0 += 32) {
             const unsigned int j = j0 + lane;
             bool hit = false;
-            if (j < n && c_cls[o + j] == cls + 1) {
+            if (j < je && c_cls[o + j] == cls + 1) {
                 const float dx = xi - c_x[o + j], dy = yi - c_y[o + j];
                 const float dist = dx * dx + dy * dy;
                 hit = dist <= size_sq;
@@ -525,16 +561,23 @@ k_orientation(const PlanDev* __restrict__ plan, const float* __restrict__ lx_pla
 }
 
 // ------------------------------------------------------------------------------------------------
-// K6: MLDB descriptor, one warp per keypoint (descriptors.rs:37-175). Lanes 0..28 own the 4+9+16
-// grid cells and accumulate their samples sequentially (k outer, l inner) exactly like the reference;
-// comparisons are packed LSB-first: grid level, then channel, then pairs i<j.
+// K6: MLDB descriptor, one warp per keypoint (descriptors.rs:37-175), in two phases per grid level:
+//   1. all 32 lanes evaluate the level's samples (400 / 441 / 400 of them: rotated position, rounded
+//      gather of Lt, Lx, Ly, rotated derivative) into shared memory, in (cell, k, l) order;
+//   2. one lane per (cell, channel) adds that cell's samples SEQUENTIALLY from shared memory (k outer,
+//      l inner, f32, exactly the reference's summation order) and divides by the sample count.
+// Comparisons are packed LSB-first: grid level, then channel, then pairs i<j.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+constexpr int kDescWarps = 8;
+constexpr int kDescMaxSamples = 448;  // 441 for the 3x3 grid of 7x7 cells (pattern 10)
+
+__global__ void __launch_bounds__(32 * kDescWarps)
 k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plane, const float* __restrict__ lx_plane,
              const float* __restrict__ ly_plane, int batch, unsigned int kp_cap, const akz_keypoint* __restrict__ kps,
              const unsigned int* __restrict__ n_kp, uint8_t* __restrict__ desc, unsigned int* __restrict__ err_flags) {
-    __shared__ float s_val[8][29 * 3];
-    __shared__ unsigned int s_bits[8][16];
+    __shared__ float s_smp[kDescWarps][3][kDescMaxSamples];
+    __shared__ float s_val[kDescWarps][29 * 3];
+    __shared__ unsigned int s_bits[kDescWarps][16];
     const int img = blockIdx.y;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned int n = min(n_kp[img], kp_cap);
@@ -543,9 +586,7 @@ k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plan
     const int pattern = plan->pattern_size;
     // sample_size per grid level: ceil(pattern * {1, 2/3, 1/2}) in f32 (descriptors.rs:50,61)
     const float pf = (float)pattern;
-    const int step0 = (int)ceilf(pf * 1.0f), step1 = (int)ceilf(pf * (2.0f / 3.0f)), step2 = (int)ceilf(pf * (1.0f / 2.0f));
-    // cells per axis actually produced by the step_by loops (descriptors.rs:102-103)
-    const int n0 = (2 * pattern + step0 - 1) / step0, n1 = (2 * pattern + step1 - 1) / step1, n2 = (2 * pattern + step2 - 1) / step2;
+    const int steps[3] = {(int)ceilf(pf * 1.0f), (int)ceilf(pf * (2.0f / 3.0f)), (int)ceilf(pf * (1.0f / 2.0f))};
     for (unsigned int kidx = blockIdx.x * (blockDim.x >> 5) + wib; kidx < n; kidx += warps) {
         const akz_keypoint kp = kps[(size_t)img * kp_cap + kidx];
         const LevelDev& lv = plan->lv[kp.class_id];
@@ -556,57 +597,76 @@ k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plan
         const float* Lt = lt_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
         const float* Lx = lx_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
         const float* Ly = ly_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
-        // which cell does this lane own?
-        int glevel = -1, ci = 0, cj = 0, step = 0, cell_in_level = 0;
-        if (lane < n0 * n0) {
-            glevel = 0; step = step0; cell_in_level = lane; ci = lane / n0; cj = lane % n0;
-        } else if (lane < n0 * n0 + n1 * n1) {
-            glevel = 1; step = step1; cell_in_level = lane - n0 * n0; ci = cell_in_level / n1; cj = cell_in_level % n1;
-        } else if (lane < n0 * n0 + n1 * n1 + n2 * n2) {
-            glevel = 2; step = step2; cell_in_level = lane - n0 * n0 - n1 * n1; ci = cell_in_level / n2; cj = cell_in_level % n2;
-        }
         bool oob = false;
-        if (glevel >= 0) {
-            const int i0 = -pattern + ci * step, j0 = -pattern + cj * step;
-            float di = 0.0f, dx = 0.0f, dy = 0.0f;
-            int nsamples = 0;
-            for (int k = i0; k < i0 + step; k++)
-                for (int l = j0; l < j0 + step; l++) {
-                    const float lf = (float)l + 0.5f, kf = (float)k + 0.5f;
-                    const float sample_y = yf + (lf * co * scale + kf * si * scale);
-                    const float sample_x = xf + (-lf * si * scale + kf * co * scale);
-                    int y1 = (int)roundf(sample_y), x1 = (int)roundf(sample_x);
-                    if (x1 < 0 || y1 < 0 || x1 >= lv.w || y1 >= lv.h) {
-                        oob = true;
-                        x1 = min(max(x1, 0), lv.w - 1);
-                        y1 = min(max(y1, 0), lv.h - 1);
+        if (lane < 16) s_bits[wib][lane] = 0;
+        int cell_base = 0, dpos_base = 0;
+#pragma unroll 1
+        for (int g = 0; g < 3; g++) {
+            const int step = steps[g];
+            const int nc = g + 2;                 // cells per axis (validated on the host: 2, 3, 4)
+            const int per_cell = step * step;
+            const int total = nc * nc * per_cell;  // <= kDescMaxSamples (validated on the host)
+            // ---- phase 1: lane owns a contiguous chunk of samples; s = cell*per_cell + kk*step + ll
+            const int chunk = (total + 31) / 32;
+            int sidx = lane * chunk;
+            const int send = min(total, sidx + chunk);
+            int cell = sidx / per_cell;
+            int rem = sidx - cell * per_cell;
+            int kk = rem / step, ll = rem - kk * step;
+            int ci = cell / nc, cj = cell - ci * nc;
+            for (; sidx < send; sidx++) {
+                const int k = -pattern + ci * step + kk, l = -pattern + cj * step + ll;
+                const float lf = (float)l + 0.5f, kf = (float)k + 0.5f;
+                const float sample_y = yf + (lf * co * scale + kf * si * scale);
+                const float sample_x = xf + (-lf * si * scale + kf * co * scale);
+                int y1 = (int)roundf(sample_y), x1 = (int)roundf(sample_x);
+                if (x1 < 0 || y1 < 0 || x1 >= lv.w || y1 >= lv.h) {
+                    oob = true;
+                    x1 = min(max(x1, 0), lv.w - 1);
+                    y1 = min(max(y1, 0), lv.h - 1);
+                }
+                const size_t at = (size_t)y1 * lv.w + x1;
+                s_smp[wib][0][sidx] = Lt[at];
+                if (nch > 1) {
+                    const float rx = Lx[at], ry = Ly[at];
+                    if (nch == 2) {
+                        s_smp[wib][1][sidx] = sqrtf(rx * rx + ry * ry);
+                    } else {
+                        const float rry = rx * co + ry * si;
+                        const float rrx = -rx * si + ry * co;
+                        s_smp[wib][1][sidx] = rrx;
+                        s_smp[wib][2][sidx] = rry;
                     }
-                    const size_t at = (size_t)y1 * lv.w + x1;
-                    di = di + Lt[at];
-                    if (nch > 1) {
-                        const float rx = Lx[at], ry = Ly[at];
-                        if (nch == 2) {
-                            dx = dx + sqrtf(rx * rx + ry * ry);
-                        } else {
-                            const float rry = rx * co + ry * si;
-                            const float rrx = -rx * si + ry * co;
-                            dx = dx + rrx;
-                            dy = dy + rry;
+                }
+                if (++ll == step) {
+                    ll = 0;
+                    if (++kk == step) {
+                        kk = 0;
+                        cell++;
+                        if (++cj == nc) {
+                            cj = 0;
+                            ci++;
                         }
                     }
-                    nsamples++;
                 }
-            const float ns = (float)nsamples;
-            s_val[wib][lane * 3 + 0] = di / ns;
-            s_val[wib][lane * 3 + 1] = dx / ns;
-            s_val[wib][lane * 3 + 2] = dy / ns;
+            }
+            __syncwarp();
+            // ---- phase 2: sequential sums per (cell, channel)
+            const float ns = (float)per_cell;
+            for (int t = lane; t < nc * nc * nch; t += 32) {
+                const int c = t / nch, ch = t - c * nch;
+                const float* v = &s_smp[wib][ch][c * per_cell];
+                float acc = 0.0f;
+                for (int r = 0; r < per_cell; r++) acc = acc + v[r];
+                s_val[wib][(cell_base + c) * 3 + ch] = acc / ns;
+            }
+            __syncwarp();
+            cell_base += nc * nc;
         }
-        if (lane < 16) s_bits[wib][lane] = 0;
-        __syncwarp();
         // comparisons: bit position = dpos (descriptors.rs:161-173)
-        int dpos_base = 0, cell_base = 0;
+        cell_base = 0;
         for (int g = 0; g < 3; g++) {
-            const int cnt = (g == 0 ? n0 * n0 : (g == 1 ? n1 * n1 : n2 * n2));
+            const int cnt = (g + 2) * (g + 2);
             const int pairs = cnt * (cnt - 1) / 2;
             for (int pos = 0; pos < nch; pos++) {
                 for (int pidx = lane; pidx < pairs; pidx += 32) {
@@ -633,7 +693,7 @@ k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plan
             unsigned int* out = (unsigned int*)(desc + ((size_t)img * kp_cap + kidx) * kDescStride);
             out[lane] = s_bits[wib][lane];
         }
-        if (oob && glevel >= 0) atomicOr(&err_flags[img], (unsigned int)kErrBounds);
+        if (oob) atomicOr(&err_flags[img], (unsigned int)kErrBounds);
         __syncwarp();
     }
 }
@@ -657,13 +717,14 @@ int launch_finalize(const Launch& L, const Plan& P, const Buffers& B) {
     float* r_x = B.r_x;
     float* r_y = B.r_y;
     dim3 g1(64, L.batch);
-    k_filter_refine<<<g1, 256, 0, L.stream>>>(B.plan_dev, B.Ldet, L.batch, L.kp_cap, B.c_x, B.c_y, B.c_cls, B.n_cache, r_x,
-                                              r_y, B.keep_flag);
+    k_class_ranges<<<L.batch, 256, 0, L.stream>>>(B.c_cls, B.n_cache, L.kp_cap, B.cls_range);
+    k_filter_refine<<<g1, 256, 0, L.stream>>>(B.plan_dev, B.Ldet, L.batch, L.kp_cap, B.c_x, B.c_y, B.c_cls, B.n_cache, B.cls_range,
+                                              r_x, r_y, B.keep_flag);
     k_keep_scan<<<L.batch, 1024, 0, L.stream>>>(B.keep_flag, B.n_cache, B.n_kp, L.kp_cap);
     dim3 g3(16, L.batch);
     k_orientation<<<g3, 128, 0, L.stream>>>(B.plan_dev, B.Lx, B.Ly, L.batch, L.kp_cap, r_x, r_y, B.c_resp, B.c_cls, B.keep_flag,
                                             B.n_cache, B.kps, B.err_flags);
-    return 3;
+    return 4;
 }
 
 int launch_descriptors(const Launch& L, const Plan& P, const Buffers& B) {
