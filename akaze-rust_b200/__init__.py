@@ -77,7 +77,7 @@ _lib = None
 # every symbol include/akaze_b200.h declares
 EXPORTS = [
     "akz_last_error", "akz_version", "akz_default_config", "akz_create", "akz_destroy", "akz_context_stream",
-    "akz_context_launch_count", "akz_context_set_limits", "akz_context_enable_timing", "akz_context_stage_times", "akz_extract_u8", "akz_extract_f32",
+    "akz_context_launch_count", "akz_context_set_limits", "akz_context_set_sub_batch", "akz_context_enable_timing", "akz_context_stage_times", "akz_extract_u8", "akz_extract_f32",
     "akz_extract_batch_u8", "akz_extract_batch_u8_device", "akz_context_device_results", "akz_features_count",
     "akz_features_keypoints", "akz_features_descriptors", "akz_features_descriptor_len",
     "akz_features_num_levels", "akz_features_level_info", "akz_features_fed_tau",
@@ -108,6 +108,7 @@ def lib():
     L.akz_context_launch_count.argtypes = [vp]
     L.akz_context_launch_count.restype = C.c_uint64
     L.akz_context_set_limits.argtypes = [vp, C.c_uint32, C.c_uint32]
+    L.akz_context_set_sub_batch.argtypes = [vp, C.c_uint32]
     L.akz_context_enable_timing.argtypes = [vp, C.c_int]
     L.akz_context_stage_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
     L.akz_extract_u8.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_size_t, C.POINTER(Config), C.POINTER(vp)]
@@ -183,29 +184,55 @@ class Features:
     def __init__(self, handle):
         L = lib()
         self._h = handle
-        n = L.akz_features_count(handle)
+        self.count = int(L.akz_features_count(handle))
         self.descriptor_len = L.akz_features_descriptor_len(handle)
-        if n:
-            kp = (C.c_uint8 * (n * KEYPOINT_DTYPE.itemsize)).from_address(L.akz_features_keypoints(handle))
-            self.keypoints = np.frombuffer(kp, KEYPOINT_DTYPE).copy()
-            d = (C.c_uint8 * (n * DESCRIPTOR_STRIDE)).from_address(L.akz_features_descriptors(handle))
-            self.descriptors_padded = np.frombuffer(d, np.uint8).reshape(n, DESCRIPTOR_STRIDE).copy()
-        else:
-            self.keypoints = np.zeros(0, KEYPOINT_DTYPE)
-            self.descriptors_padded = np.zeros((0, DESCRIPTOR_STRIDE), np.uint8)
-        # Descriptor.vector of the reference has (162*channels+7)/8 bytes (descriptors.rs:42-46)
-        self.descriptors = self.descriptors_padded[:, :self.descriptor_len]
         self.contrast_factor = L.akz_features_contrast_factor(handle)
         self.num_candidates = L.akz_features_num_candidates(handle)
         self.num_cache = L.akz_features_num_cache(handle)
-        self.evolutions = []
-        for lv in range(L.akz_features_num_levels(handle)):
-            info = LevelInfo()
-            _check(L.akz_features_level_info(handle, lv, C.byref(info)))
-            taus = np.zeros(info.n_steps, np.float64)
-            if info.n_steps:
-                _check(L.akz_features_fed_tau(handle, lv, taus.ctypes.data_as(C.POINTER(C.c_double)), info.n_steps))
-            self.evolutions.append(EvolutionStep(self, lv, info, taus))
+        self._kp = self._desc = self._evo = None
+
+    # keypoints / descriptors are copied out of the library-owned (pinned) buffers on first access, so the
+    # arrays stay valid after close(); `count` is free
+    @property
+    def keypoints(self):
+        if self._kp is None:
+            n = self.count
+            if n:
+                kp = (C.c_uint8 * (n * KEYPOINT_DTYPE.itemsize)).from_address(lib().akz_features_keypoints(self._h))
+                self._kp = np.frombuffer(kp, KEYPOINT_DTYPE).copy()
+            else:
+                self._kp = np.zeros(0, KEYPOINT_DTYPE)
+        return self._kp
+
+    @property
+    def descriptors_padded(self):
+        if self._desc is None:
+            n = self.count
+            if n:
+                d = (C.c_uint8 * (n * DESCRIPTOR_STRIDE)).from_address(lib().akz_features_descriptors(self._h))
+                self._desc = np.frombuffer(d, np.uint8).reshape(n, DESCRIPTOR_STRIDE).copy()
+            else:
+                self._desc = np.zeros((0, DESCRIPTOR_STRIDE), np.uint8)
+        return self._desc
+
+    @property
+    def descriptors(self):
+        """Descriptor.vector of the reference has (162*channels+7)/8 bytes (descriptors.rs:42-46)."""
+        return self.descriptors_padded[:, :self.descriptor_len]
+
+    @property
+    def evolutions(self):
+        if self._evo is None:
+            L = lib()
+            self._evo = []
+            for lv in range(L.akz_features_num_levels(self._h)):
+                info = LevelInfo()
+                _check(L.akz_features_level_info(self._h, lv, C.byref(info)))
+                taus = np.zeros(info.n_steps, np.float64)
+                if info.n_steps:
+                    _check(L.akz_features_fed_tau(self._h, lv, taus.ctypes.data_as(C.POINTER(C.c_double)), info.n_steps))
+                self._evo.append(EvolutionStep(self, lv, info, taus))
+        return self._evo
 
     def evolution(self, level, kind):
         k = IMAGE_KINDS[kind] if isinstance(kind, str) else int(kind)
@@ -216,12 +243,20 @@ class Features:
 
     def close(self):
         if self._h:
+            # materialise what callers may still read after close (cheap; evolutions' images are not kept)
+            self.keypoints, self.descriptors_padded, self.evolutions  # noqa: B018
+            lib().akz_features_free(self._h)
+            self._h = None
+
+    def release(self):
+        """Frees the handle without copying anything out (throughput loops that only need `count`)."""
+        if self._h:
             lib().akz_features_free(self._h)
             self._h = None
 
     def __del__(self):
         try:
-            self.close()
+            self.release()
         except Exception:
             pass
 
@@ -273,6 +308,10 @@ class Engine:
     @property
     def launch_count(self):
         return lib().akz_context_launch_count(self._h)
+
+    def set_sub_batch(self, images):
+        """Images per pipeline sub-batch (akz_context_set_sub_batch)."""
+        _check(lib().akz_context_set_sub_batch(self._h, int(images)))
 
     def enable_timing(self, on=True):
         _check(lib().akz_context_enable_timing(self._h, int(on)))

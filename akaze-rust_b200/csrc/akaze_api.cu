@@ -10,6 +10,7 @@
 // and the orchestration of create_nonlinear_scale_space / find_image_keypoints / extract_features
 // (akaze/src/lib.rs:49-194) as a fixed sequence of kernel launches on one stream.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -283,6 +284,27 @@ struct Lane {
     bool busy = false;
 };
 
+// per-image statistics mirrored into pinned host memory after stage B of each sub-batch
+struct HostStats {
+    unsigned int* n_kp = nullptr;       // [n]
+    unsigned int* n_cache = nullptr;
+    unsigned int* n_cand = nullptr;
+    unsigned int* err = nullptr;
+    double* kcontrast = nullptr;        // [n][kMaxLevels]
+    void* base = nullptr;
+    int alloc_n = 0;
+};
+
+// pinned host slab that receives the keypoints + descriptors of one sub-batch; shared by the akz_features
+// handles cut from it and recycled by the context's pool once they have all been freed
+struct PinnedChunk {
+    void* p = nullptr;
+    size_t cap = 0;
+    ~PinnedChunk() {
+        if (p) cudaFreeHost(p);
+    }
+};
+
 struct Results {
     akz_keypoint* kps = nullptr;        // [n][kp_cap]
     uint8_t* desc = nullptr;            // [n][kp_cap][64]
@@ -305,7 +327,11 @@ struct akz_context {
     cudaStream_t stream = nullptr;     // stage A, copies, and the stream callers may time on
     cudaStream_t stream_kp = nullptr;  // stage B
     cudaStream_t stream_copy = nullptr;  // host -> device staging of the inputs, one event per sub-batch
+    cudaStream_t stream_d2h = nullptr;   // device -> host copies of the results, sub-batch by sub-batch
     std::vector<cudaEvent_t> ev_copy;
+    std::vector<cudaEvent_t> ev_stats;   // statistics of sub-batch i are in pinned memory (implies its stage B is done)
+    HostStats hs;
+    std::vector<std::shared_ptr<PinnedChunk>> pinned_pool;
     uint64_t launches = 0;
     uint64_t generation = 0;
     bool have_plan = false;
@@ -313,6 +339,7 @@ struct akz_context {
     Lane lane[2];
     Results res;
     int cur_batch = 0;
+    uint32_t n_sub_batches = 0;
     // per-stage timing
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
@@ -333,9 +360,11 @@ struct akz_features {
     akz_context* ctx = nullptr;
     uint64_t generation = 0;
     int img = 0, batch = 0;
-    std::vector<akz_keypoint> kps;
-    std::vector<uint8_t> desc;
-    std::vector<LevelHost> levels;
+    std::shared_ptr<PinnedChunk> chunk;                      // owns the memory kps/desc point into
+    const akz_keypoint* kps = nullptr;
+    const uint8_t* desc = nullptr;
+    size_t n = 0;
+    std::shared_ptr<const std::vector<LevelHost>> levels;   // shared by all features of one call
     uint32_t desc_len = 0;
     double contrast = 0.0;
     uint64_t n_cand = 0, n_cache = 0;
@@ -437,6 +466,19 @@ static int ensure_results(akz_context* c, int n) {
     CK(dalloc(R.allocs, &R.in_u8, n0));
     CK(dalloc(R.allocs, &R.in_f32, (size_t)c->plan.w * c->plan.h));  // akz_extract_f32 is single-image
     R.alloc_n = n;
+    HostStats& H = c->hs;
+    if (n > H.alloc_n) {
+        if (H.base) cudaFreeHost(H.base);
+        H = HostStats();
+        const size_t bytes = nb * (kMaxLevels * sizeof(double) + 4 * sizeof(unsigned int));
+        CK(cudaHostAlloc(&H.base, bytes, cudaHostAllocDefault));
+        H.kcontrast = (double*)H.base;
+        H.n_kp = (unsigned int*)(H.kcontrast + nb * kMaxLevels);
+        H.n_cache = H.n_kp + nb;
+        H.n_cand = H.n_cache + nb;
+        H.err = H.n_cand + nb;
+        H.alloc_n = n;
+    }
     return AKZ_OK;
 }
 
@@ -574,8 +616,25 @@ static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8
         STAGE(AKZ_STAGE_FINALIZE, c->stream_kp, launch_finalize(LB, P, B));
         STAGE(AKZ_STAGE_DESCRIPTOR, c->stream_kp, launch_descriptors(LB, P, B));
         CK(cudaEventRecord(ln.ev_done, c->stream_kp));
+        // timing mode serialises the two stages so that every stage's event pair brackets its kernels alone
+        if (c->timing) CK(cudaStreamWaitEvent(c->stream, ln.ev_done, 0));
         ln.busy = true;
+        // mirror this sub-batch's statistics into pinned memory; the host reads them after ev_stats[sb]
+        const HostStats& H = c->hs;
+        CK(cudaMemcpyAsync(H.n_kp + i0, B.n_kp, cnt * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream_kp));
+        CK(cudaMemcpyAsync(H.n_cache + i0, B.n_cache, cnt * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream_kp));
+        CK(cudaMemcpyAsync(H.n_cand + i0, B.n_cand_total, cnt * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream_kp));
+        CK(cudaMemcpyAsync(H.err + i0, B.err_flags, cnt * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream_kp));
+        CK(cudaMemcpyAsync(H.kcontrast + (size_t)i0 * kMaxLevels, B.kcontrast, (size_t)cnt * kMaxLevels * sizeof(double),
+                           cudaMemcpyDeviceToHost, c->stream_kp));
+        while (c->ev_stats.size() <= sb) {
+            cudaEvent_t e;
+            CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            c->ev_stats.push_back(e);
+        }
+        CK(cudaEventRecord(c->ev_stats[sb], c->stream_kp));
     }
+    c->n_sub_batches = (n + m - 1) / m;
 #undef STAGE
     for (int l = 0; l < 2; l++)
         if (c->lane[l].busy) {
@@ -587,38 +646,95 @@ static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8
     return AKZ_OK;
 }
 
-struct BatchStats {
-    std::vector<unsigned int> n_kp, n_cache, n_cand, err;
-    std::vector<double> kcontrast;
-};
-
-static int fetch_stats(akz_context* c, uint32_t n, BatchStats* s) {
-    const Results& R = c->res;
-    s->n_kp.resize(n);
-    s->n_cache.resize(n);
-    s->n_cand.resize(n);
-    s->err.resize(n);
-    s->kcontrast.resize((size_t)n * kMaxLevels);
-    CK(cudaMemcpyAsync(s->n_kp.data(), R.n_kp, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(s->n_cache.data(), R.n_cache, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(s->n_cand.data(), R.n_cand, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(s->err.data(), R.err, n * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaMemcpyAsync(s->kcontrast.data(), R.kcontrast, (size_t)n * kMaxLevels * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CK(cudaStreamSynchronize(c->stream));
-    if (c->timing) harvest_timing(c);
-    for (uint32_t i = 0; i < n; i++) {
-        if (s->err[i] & kErrCandOverflow) return fail(AKZ_ERR_CAPACITY, "candidate list overflow (raise max_candidates)");
-        if (s->err[i] & kErrKpOverflow) return fail(AKZ_ERR_CAPACITY, "keypoint cache overflow (raise max_keypoints)");
-        if (s->err[i] & kErrBounds) return fail(AKZ_ERR_BOUNDS, "a descriptor/orientation sample fell outside the image (the reference panics here)");
+static int check_err_flags(const akz_context* c, uint32_t i0, uint32_t i1) {
+    for (uint32_t i = i0; i < i1; i++) {
+        const unsigned int e = c->hs.err[i];
+        if (e & kErrCandOverflow) return fail(AKZ_ERR_CAPACITY, "candidate list overflow (raise max_candidates)");
+        if (e & kErrKpOverflow) return fail(AKZ_ERR_CAPACITY, "keypoint cache overflow (raise max_keypoints)");
+        if (e & kErrBounds) return fail(AKZ_ERR_BOUNDS, "a descriptor/orientation sample fell outside the image (the reference panics here)");
     }
     return AKZ_OK;
 }
 
+// waits for the whole call; the per-image statistics are then valid in c->hs
+static int finish_device_call(akz_context* c, uint32_t n) {
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaStreamSynchronize(c->stream_kp));
+    if (c->timing) harvest_timing(c);
+    return check_err_flags(c, 0, n);
+}
+
+// a pinned slab of at least `bytes` from the pool (slabs whose features have all been freed are reused)
+static int get_chunk(akz_context* c, size_t bytes, std::shared_ptr<PinnedChunk>* out) {
+    std::shared_ptr<PinnedChunk> best;
+    for (auto& ch : c->pinned_pool)
+        if (ch.use_count() == 1 && ch->cap >= bytes && (!best || ch->cap < best->cap)) best = ch;
+    if (!best) {
+        // drop idle slabs that were too small before growing the pool
+        std::vector<std::shared_ptr<PinnedChunk>> keep;
+        for (auto& ch : c->pinned_pool)
+            if (ch.use_count() > 1 || ch->cap >= bytes) keep.push_back(ch);
+        c->pinned_pool.swap(keep);
+        best = std::make_shared<PinnedChunk>();
+        const size_t cap = std::max<size_t>(bytes + bytes / 4, 1 << 16);
+        cudaError_t e = cudaHostAlloc(&best->p, cap, cudaHostAllocDefault);
+        if (e != cudaSuccess) return fail(AKZ_ERR_NOMEM, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+        best->cap = cap;
+        c->pinned_pool.push_back(best);
+    }
+    *out = best;
+    return AKZ_OK;
+}
+
+// Host side of a host-buffer call, sub-batch by sub-batch while later sub-batches are still running:
+// wait for the sub-batch's statistics, then pull exactly n_kp keypoints + descriptors per image into one
+// pinned slab on the D2H stream. Handles are cut from the slabs at the end.
 static int collect_features(akz_context* c, uint32_t n, akz_features** outs) {
-    BatchStats st;
-    int rc = fetch_stats(c, n, &st);
-    if (rc != AKZ_OK) return rc;
     const Results& R = c->res;
+    const HostStats& H = c->hs;
+    const uint32_t m = sub_batch_of(c, n);
+    struct Slot {
+        std::shared_ptr<PinnedChunk> chunk;
+        size_t kp_off, desc_off;
+    };
+    std::vector<Slot> slots(n);
+    int rc = AKZ_OK;
+    for (uint32_t i0 = 0, sb = 0; i0 < n && rc == AKZ_OK; i0 += m, sb++) {
+        const uint32_t i1 = std::min(n, i0 + m);
+        CK(cudaEventSynchronize(c->ev_stats[sb]));
+        rc = check_err_flags(c, i0, i1);
+        if (rc != AKZ_OK) break;
+        size_t total = 0;
+        for (uint32_t i = i0; i < i1; i++) total += H.n_kp[i];
+        std::shared_ptr<PinnedChunk> chunk;
+        rc = get_chunk(c, total * (sizeof(akz_keypoint) + kDescStride) + 64, &chunk);
+        if (rc != AKZ_OK) break;
+        // descriptors first (64-byte rows stay 64-byte aligned), keypoints behind them
+        size_t doff = 0, koff = total * kDescStride;
+        CK(cudaStreamWaitEvent(c->stream_d2h, c->ev_stats[sb], 0));
+        for (uint32_t i = i0; i < i1; i++) {
+            const size_t nk = H.n_kp[i];
+            slots[i] = Slot{chunk, koff, doff};
+            if (nk) {
+                CK(cudaMemcpyAsync((char*)chunk->p + doff, R.desc + (size_t)i * c->kp_cap * kDescStride, nk * kDescStride,
+                                   cudaMemcpyDeviceToHost, c->stream_d2h));
+                CK(cudaMemcpyAsync((char*)chunk->p + koff, R.kps + (size_t)i * c->kp_cap, nk * sizeof(akz_keypoint),
+                                   cudaMemcpyDeviceToHost, c->stream_d2h));
+            }
+            doff += nk * kDescStride;
+            koff += nk * sizeof(akz_keypoint);
+        }
+    }
+    // the call is over (also on error paths): nothing of it may still be in flight when we return
+    cudaError_t e1 = cudaStreamSynchronize(c->stream);
+    cudaError_t e2 = cudaStreamSynchronize(c->stream_kp);
+    cudaError_t e3 = cudaStreamSynchronize(c->stream_d2h);
+    if (c->timing) harvest_timing(c);
+    if (rc != AKZ_OK) return rc;
+    CK(e1);
+    CK(e2);
+    CK(e3);
+    auto levels = std::make_shared<const std::vector<LevelHost>>(c->plan.host);
     std::vector<std::unique_ptr<akz_features>> fs;
     for (uint32_t i = 0; i < n; i++) {
         std::unique_ptr<akz_features> f(new akz_features());
@@ -626,21 +742,17 @@ static int collect_features(akz_context* c, uint32_t n, akz_features** outs) {
         f->generation = c->generation;
         f->img = (int)i;
         f->batch = (int)n;
-        f->levels = c->plan.host;
+        f->levels = levels;
         f->desc_len = (uint32_t)c->plan.dev.desc_len;
-        f->contrast = st.kcontrast[(size_t)i * kMaxLevels];
-        f->n_cand = st.n_cand[i];
-        f->n_cache = st.n_cache[i];
-        const size_t nk = st.n_kp[i];
-        f->kps.resize(nk);
-        f->desc.resize(nk * kDescStride);
-        if (nk) {
-            CK(cudaMemcpyAsync(f->kps.data(), R.kps + (size_t)i * c->kp_cap, nk * sizeof(akz_keypoint), cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaMemcpyAsync(f->desc.data(), R.desc + (size_t)i * c->kp_cap * kDescStride, nk * kDescStride, cudaMemcpyDeviceToHost, c->stream));
-        }
+        f->contrast = H.kcontrast[(size_t)i * kMaxLevels];
+        f->n_cand = H.n_cand[i];
+        f->n_cache = H.n_cache[i];
+        f->n = H.n_kp[i];
+        f->chunk = slots[i].chunk;
+        f->kps = (const akz_keypoint*)((const char*)slots[i].chunk->p + slots[i].kp_off);
+        f->desc = (const uint8_t*)slots[i].chunk->p + slots[i].desc_off;
         fs.push_back(std::move(f));
     }
-    CK(cudaStreamSynchronize(c->stream));
     for (uint32_t i = 0; i < n; i++) outs[i] = fs[i].release();
     return AKZ_OK;
 }
@@ -684,9 +796,14 @@ int akz_create(int device, uint32_t max_width, uint32_t max_height, uint32_t max
     c->max_h = max_height;
     c->max_batch = max_batch;
     c->flags = flags;
+    if (const char* sbe = getenv("AKZ_SUB_BATCH")) {
+        const int v = atoi(sbe);
+        if (v > 0) c->sub_batch = (uint32_t)v;
+    }
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->stream_kp, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->stream_d2h, cudaStreamNonBlocking));
     CK(init_detector_attributes());
     CK(init_keypoint_attributes());
     *out = c.release();
@@ -705,7 +822,12 @@ void akz_destroy(akz_context* c) {
     }
     cudaStreamDestroy(c->stream_kp);
     for (cudaEvent_t e : c->ev_copy) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_stats) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream_copy);
+    cudaStreamSynchronize(c->stream_d2h);
+    cudaStreamDestroy(c->stream_d2h);
+    if (c->hs.base) cudaFreeHost(c->hs.base);
+    c->pinned_pool.clear();  // slabs still referenced by live akz_features are freed with the last of them
     cudaFree(c->m_q);
     cudaFree(c->m_db);
     cudaFree(c->m_parts);
@@ -750,6 +872,15 @@ int akz_context_set_limits(akz_context* c, uint32_t max_candidates, uint32_t max
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->stream_kp);
     free_buffers(c);
+    return AKZ_OK;
+}
+
+int akz_context_set_sub_batch(akz_context* c, uint32_t images) {
+    if (!c || images == 0) return fail(AKZ_ERR_INVALID, "bad sub-batch size");
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->stream_kp);
+    c->sub_batch = images;
     return AKZ_OK;
 }
 
@@ -803,10 +934,9 @@ int akz_extract_batch_u8_device(akz_context* c, uint32_t n, const void* d_grays,
     if (rc != AKZ_OK) return rc;
     rc = run_pipeline(c, n, d_grays, true, stride);
     if (rc != AKZ_OK) return rc;
-    BatchStats st;
-    rc = fetch_stats(c, n, &st);
+    rc = finish_device_call(c, n);
     if (rc != AKZ_OK) return rc;
-    for (uint32_t i = 0; i < n; i++) counts[i] = st.n_kp[i];
+    for (uint32_t i = 0; i < n; i++) counts[i] = c->hs.n_kp[i];
     return AKZ_OK;
 }
 
@@ -818,19 +948,19 @@ int akz_context_device_results(akz_context* c, void** d_keypoints, void** d_desc
     return AKZ_OK;
 }
 
-uint64_t akz_features_count(const akz_features* f) { return f ? f->kps.size() : 0; }
-const akz_keypoint* akz_features_keypoints(const akz_features* f) { return f ? f->kps.data() : nullptr; }
-const uint8_t* akz_features_descriptors(const akz_features* f) { return f ? f->desc.data() : nullptr; }
+uint64_t akz_features_count(const akz_features* f) { return f ? f->n : 0; }
+const akz_keypoint* akz_features_keypoints(const akz_features* f) { return f ? f->kps : nullptr; }
+const uint8_t* akz_features_descriptors(const akz_features* f) { return f ? f->desc : nullptr; }
 uint32_t akz_features_descriptor_len(const akz_features* f) { return f ? f->desc_len : 0; }
-uint32_t akz_features_num_levels(const akz_features* f) { return f ? (uint32_t)f->levels.size() : 0; }
+uint32_t akz_features_num_levels(const akz_features* f) { return f ? (uint32_t)f->levels->size() : 0; }
 int akz_features_level_info(const akz_features* f, uint32_t level, akz_level_info* out) {
-    if (!f || !out || level >= f->levels.size()) return fail(AKZ_ERR_INVALID, "bad level");
-    *out = f->levels[level].info;
+    if (!f || !out || level >= f->levels->size()) return fail(AKZ_ERR_INVALID, "bad level");
+    *out = (*f->levels)[level].info;
     return AKZ_OK;
 }
 int akz_features_fed_tau(const akz_features* f, uint32_t level, double* out, uint32_t cap) {
-    if (!f || level >= f->levels.size() || (!out && cap)) return fail(AKZ_ERR_INVALID, "bad level");
-    const std::vector<double>& t = f->levels[level].tau;
+    if (!f || level >= f->levels->size() || (!out && cap)) return fail(AKZ_ERR_INVALID, "bad level");
+    const std::vector<double>& t = (*f->levels)[level].tau;
     for (uint32_t i = 0; i < cap && i < t.size(); i++) out[i] = t[i];
     return AKZ_OK;
 }
@@ -839,7 +969,7 @@ uint64_t akz_features_num_candidates(const akz_features* f) { return f ? f->n_ca
 uint64_t akz_features_num_cache(const akz_features* f) { return f ? f->n_cache : 0; }
 
 int akz_features_evolution_download(const akz_features* f, uint32_t level, int kind, float* dst) {
-    if (!f || !dst || level >= f->levels.size()) return fail(AKZ_ERR_INVALID, "bad argument");
+    if (!f || !dst || level >= f->levels->size()) return fail(AKZ_ERR_INVALID, "bad argument");
     akz_context* c = f->ctx;
     if (!(c->flags & AKZ_KEEP_EVOLUTIONS)) return fail(AKZ_ERR_INVALID, "context was created without AKZ_KEEP_EVOLUTIONS");
     if (c->generation != f->generation) return fail(AKZ_ERR_INVALID, "evolutions were overwritten by a later extraction");

@@ -163,6 +163,7 @@ k_dedup(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ cand,
 // busiest level has more than kPool candidates is left to the global-memory kernel above.
 // ------------------------------------------------------------------------------------------------
 constexpr int kPool = 4096;
+constexpr int kGroups = 8;   // candidates decided per step of the cache pass (lanes per candidate = 32 / kGroups)
 constexpr int kMaxGridCells = 8448;
 constexpr unsigned short kNil = 0xffffu;
 
@@ -239,6 +240,13 @@ k_dedup_smem(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ 
             nx_flat = cl[beg + lane];
             nx_resp = fabsf(ldet[nx_flat]);
         }
+        // kGroups candidates are decided per step, one per group of 32/kGroups lanes, against the state
+        // BEFORE the step; a candidate whose decision could be changed by the write of an earlier candidate
+        // of the same step (see the conflict rule below) ends the step: only the candidates before it
+        // commit, it is re-decided at the head of the next step. The sequential semantics is kept exactly.
+        constexpr int GL = 32 / kGroups;  // lanes per group
+        const int grp = lane / GL, sub = lane % GL;
+        const bool leader = sub == 0;
         for (unsigned int base = beg; base < end && !overflow; base += 32) {
             const unsigned int my_flat = nx_flat;
             const float my_resp = nx_resp;
@@ -247,92 +255,109 @@ k_dedup_smem(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ 
                 nx_resp = fabsf(ldet[nx_flat]);
             }
             const int n_here = min(32u, end - base);
-            for (int k = 0; k < n_here; k++) {
-                const unsigned int flat = __shfl_sync(FULL, my_flat, k);
-                const float resp = __shfl_sync(FULL, my_resp, k);
+            int k0 = 0;
+            while (k0 < n_here) {
+                const int k = k0 + grp;
+                const bool active = k < n_here;
+                const unsigned int flat = __shfl_sync(FULL, my_flat, k & 31);
+                const float resp = __shfl_sync(FULL, my_resp, k & 31);
                 const int px = (int)(flat % (unsigned int)lv.w), py = (int)(flat / (unsigned int)lv.w);
                 const float qx = (float)px * ratio, qy = (float)py * ratio;
-                const int cx0 = max(0, ((int)floorf(qx - size) - 1) >> gshift);
-                const int cx1 = min(gw - 1, ((int)floorf(qx + size) + 1) >> gshift);
-                const int cy0 = max(0, ((int)floorf(qy - size) - 1) >> gshift);
-                const int cy1 = min(gh - 1, ((int)floorf(qy + size) + 1) >> gshift);
-                const int nx = cx1 - cx0 + 1;
-                const int ncell = nx * (cy1 - cy0 + 1);
-                const int ntot = (L > 0) ? 2 * ncell : ncell;
                 unsigned int best = 0xffffffffu;  // lowest matching slot
                 unsigned int best_ref = 0;        // (pool << 16) | pool index of that slot
-                for (int c = lane; c < ntot; c += 32) {
-                    const int which = (c >= ncell) ? prv : cur;
-                    const int cc = (c >= ncell) ? c - ncell : c;
-                    const int cell = (cy0 + cc / nx) * gw + (cx0 + cc % nx);
-                    unsigned short e = S.heads[which][cell];
-                    while (e != kNil) {
-                        const float dx = qx - S.px[which][e], dy = qy - S.py[which][e];
-                        const float dist = dx * dx + dy * dy;
-                        const unsigned int s = S.pslot[which][e];
-                        if (dist <= size_sq && s < best) {
-                            best = s;
-                            best_ref = ((unsigned int)which << 16) | e;
-                        }
-                        e = S.pnext[which][e];
-                    }
-                }
-                const unsigned int gbest = __reduce_min_sync(FULL, best);
-                bool append = false;
-                unsigned int slot = 0;
-                if (gbest == 0xffffffffu) {
-                    if (n >= kp_cap) {
-                        overflow = true;
-                        break;
-                    }
-                    slot = n++;
-                    append = true;
-                } else {
-                    // the lane that found the winning slot publishes where it lives
-                    const unsigned int owner = __ffs(__ballot_sync(FULL, best == gbest)) - 1;
-                    const unsigned int ref = __shfl_sync(FULL, best_ref, owner);
-                    const int bw = (int)(ref >> 16);
-                    const unsigned short be = (unsigned short)(ref & 0xffffu);
-                    if (resp > S.presp[bw][be]) {  // scale_space_extrema.rs:67
-                        slot = gbest;
-                        append = true;
-                        if (lane == 0) {
-                            // unlink the old occupant from its cell list and mark it dead
-                            const int ocx = min(gw - 1, max(0, (int)S.px[bw][be] >> gshift));
-                            const int ocy = min(gh - 1, max(0, (int)S.py[bw][be] >> gshift));
-                            const int ocell = ocy * gw + ocx;
-                            unsigned short e = S.heads[bw][ocell];
-                            if (e == be) {
-                                S.heads[bw][ocell] = S.pnext[bw][be];
-                            } else {
-                                while (e != kNil) {
-                                    const unsigned short nxt = S.pnext[bw][e];
-                                    if (nxt == be) {
-                                        S.pnext[bw][e] = S.pnext[bw][be];
-                                        break;
-                                    }
-                                    e = nxt;
-                                }
+                if (active) {
+                    const int cx0 = max(0, ((int)floorf(qx - size) - 1) >> gshift);
+                    const int cx1 = min(gw - 1, ((int)floorf(qx + size) + 1) >> gshift);
+                    const int cy0 = max(0, ((int)floorf(qy - size) - 1) >> gshift);
+                    const int cy1 = min(gh - 1, ((int)floorf(qy + size) + 1) >> gshift);
+                    const int nx = cx1 - cx0 + 1;
+                    const int ncell = nx * (cy1 - cy0 + 1);
+                    const int ntot = (L > 0) ? 2 * ncell : ncell;
+                    for (int c = sub; c < ntot; c += GL) {
+                        const int which = (c >= ncell) ? prv : cur;
+                        const int cc = (c >= ncell) ? c - ncell : c;
+                        const int cell = (cy0 + cc / nx) * gw + (cx0 + cc % nx);
+                        unsigned short e = S.heads[which][cell];
+                        while (e != kNil) {
+                            const float dx = qx - S.px[which][e], dy = qy - S.py[which][e];
+                            const float dist = dx * dx + dy * dy;
+                            const unsigned int s = S.pslot[which][e];  // 0xffffffff = replaced (dead) entry: never < best
+                            if (dist <= size_sq && s < best) {
+                                best = s;
+                                best_ref = ((unsigned int)which << 16) | e;
                             }
-                            S.pslot[bw][be] = 0xffffffffu;
+                            e = S.pnext[which][e];
                         }
                     }
                 }
-                if (append) {
-                    const int at = cnt[cur]++;  // <= candidates of this level <= kPool
-                    if (lane == 0) {
-                        const float fx = (float)px * ratio + hr, fy = (float)py * ratio + hr;  // :89-92
-                        S.px[cur][at] = fx;
-                        S.py[cur][at] = fy;
-                        S.presp[cur][at] = resp;
-                        S.pslot[cur][at] = slot;
-                        const int ncx = min(gw - 1, max(0, (int)fx >> gshift));
-                        const int ncy = min(gh - 1, max(0, (int)fy >> gshift));
-                        const int ncl = ncy * gw + ncx;
-                        S.pnext[cur][at] = S.heads[cur][ncl];
-                        S.heads[cur][ncl] = (unsigned short)at;
+#pragma unroll
+                for (int o = 1; o < GL; o <<= 1) {
+                    const unsigned int ob = __shfl_xor_sync(FULL, best, o);
+                    const unsigned int orf = __shfl_xor_sync(FULL, best_ref, o);
+                    if (ob < best) {
+                        best = ob;
+                        best_ref = orf;
                     }
                 }
+                // decision against the pre-step state: 0 = drop, 1 = append, 2 = replace slot `best`
+                const int bw = (int)(best_ref >> 16);
+                const unsigned short be = (unsigned short)(best_ref & 0xffffu);
+                int act = 0;
+                if (active) {
+                    if (best == 0xffffffffu) act = 1;
+                    else if (resp > S.presp[bw][be]) act = 2;  // scale_space_extrema.rs:67
+                }
+                const float fx = (float)px * ratio + hr, fy = (float)py * ratio + hr;  // :89-92
+                // conflict rule: an earlier candidate a of this step that writes changes the decision of b only if
+                // its new entry lies within `size` of b (b would see it), or it replaces the very slot b matched
+                bool conflict = false;
+#pragma unroll
+                for (int a = 0; a < kGroups - 1; a++) {
+                    const int a_act = __shfl_sync(FULL, act, a * GL);
+                    const float a_fx = __shfl_sync(FULL, fx, a * GL), a_fy = __shfl_sync(FULL, fy, a * GL);
+                    const unsigned int a_best = __shfl_sync(FULL, best, a * GL);
+                    if (a < grp && a_act != 0 && active) {
+                        const float dx = qx - a_fx, dy = qy - a_fy;
+                        const float dist = dx * dx + dy * dy;
+                        if (dist <= size_sq || (a_act == 2 && a_best == best)) conflict = true;
+                    }
+                }
+                const unsigned int cmask = __ballot_sync(FULL, conflict && leader);
+                const int n_act = min(kGroups, n_here - k0);
+                const int n_commit = cmask ? min(n_act, (__ffs(cmask) - 1) / GL) : n_act;  // >= 1: group 0 never conflicts
+                const bool commits = leader && grp < n_commit;
+                const unsigned int amask = __ballot_sync(FULL, commits && act == 1);
+                const unsigned int wmask = __ballot_sync(FULL, commits && act != 0);
+                const unsigned int lt = (1u << lane) - 1u;
+                if (n + __popc(amask) > kp_cap) {
+                    overflow = true;
+                    break;
+                }
+                if (commits && act != 0) {
+                    const unsigned int slot = (act == 1) ? n + __popc(amask & lt) : best;
+                    const int at = cnt[cur] + __popc(wmask & lt);  // <= candidates of this level <= kPool
+                    if (act == 2) S.pslot[bw][be] = 0xffffffffu;  // the old occupant is dead; it stays on its cell list
+                    S.px[cur][at] = fx;
+                    S.py[cur][at] = fy;
+                    S.presp[cur][at] = resp;
+                    S.pslot[cur][at] = slot;
+                    const int ncx = min(gw - 1, max(0, (int)fx >> gshift));
+                    const int ncy = min(gh - 1, max(0, (int)fy >> gshift));
+                    const int ncl = ncy * gw + ncx;
+                    // writers that hash to the same cell link in lane order, the others all at once
+                    const unsigned int same = __match_any_sync(wmask, ncl);
+                    const int rank = __popc(same & lt), nsame = __popc(same);
+                    for (int r = 0; r < nsame; r++) {
+                        if (r == rank) {
+                            S.pnext[cur][at] = S.heads[cur][ncl];
+                            S.heads[cur][ncl] = (unsigned short)at;
+                        }
+                        __syncwarp(same);
+                    }
+                }
+                n += __popc(amask);
+                cnt[cur] += __popc(wmask);
+                k0 += n_commit;
                 __syncwarp();
             }
         }

@@ -123,6 +123,11 @@ int akz_context_stage_times(akz_context *ctx, double *ms, uint64_t *launches, in
  * truncating. Defaults: 262144 candidates, 65536 keypoints. Call before the first extraction. */
 int akz_context_set_limits(akz_context *ctx, uint32_t max_candidates, uint32_t max_keypoints);
 
+/* A call of n images is cut into sub-batches of `images` that flow through a two-stage software pipeline
+ * (stencil stages of sub-batch i+1 overlap the keypoint stages and the result download of sub-batch i).
+ * Default 64; memory per in-flight image is about 0.2 GB at 1080p. Environment override: AKZ_SUB_BATCH. */
+int akz_context_set_sub_batch(akz_context *ctx, uint32_t images);
+
 /* ---- extraction: replaces akaze::extract_features (akaze/src/lib.rs:167-194) from the
  *      GrayFloatImage on; decode + to_luma (lib.rs:171, image.rs:128) stay with the host ------- */
 /* gray: 8-bit luma, row stride in bytes; the u8 -> unit float conversion of
@@ -132,7 +137,9 @@ int akz_extract_u8(akz_context *ctx, const uint8_t *gray, uint32_t width, uint32
 /* unit_gray: exactly the GrayFloatImage buffer of image.rs:127-140 (row-major, width*height). */
 int akz_extract_f32(akz_context *ctx, const float *unit_gray, uint32_t width, uint32_t height,
                     const akz_config *cfg, akz_features **out);
-/* n images of identical size; outs[n] receives one handle per image. */
+/* n images of identical size; outs[n] receives one handle per image. Uploads, kernels and result downloads
+ * of consecutive sub-batches overlap; keypoints and descriptors land in pinned host slabs owned by the
+ * handles (pass pinned images for fully asynchronous uploads). */
 int akz_extract_batch_u8(akz_context *ctx, uint32_t n, const uint8_t *const *grays, uint32_t width,
                          uint32_t height, size_t stride, const akz_config *cfg, akz_features **outs);
 /* Throughput path: the n images already sit in device memory (n * height * stride bytes, contiguous);
