@@ -77,7 +77,7 @@ _lib = None
 # every symbol include/akaze_b200.h declares
 EXPORTS = [
     "akz_last_error", "akz_version", "akz_default_config", "akz_create", "akz_destroy", "akz_context_stream",
-    "akz_context_launch_count", "akz_context_set_limits", "akz_context_set_sub_batch", "akz_context_enable_timing", "akz_context_stage_times", "akz_extract_u8", "akz_extract_f32",
+    "akz_context_launch_count", "akz_context_set_limits", "akz_context_set_sub_batch", "akz_context_set_match_path", "akz_context_enable_timing", "akz_context_stage_times", "akz_extract_u8", "akz_extract_f32",
     "akz_extract_batch_u8", "akz_extract_batch_u8_device", "akz_context_device_results", "akz_features_count",
     "akz_features_keypoints", "akz_features_descriptors", "akz_features_descriptor_len",
     "akz_features_num_levels", "akz_features_level_info", "akz_features_fed_tau",
@@ -109,6 +109,7 @@ def lib():
     L.akz_context_launch_count.restype = C.c_uint64
     L.akz_context_set_limits.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.akz_context_set_sub_batch.argtypes = [vp, C.c_uint32]
+    L.akz_context_set_match_path.argtypes = [vp, C.c_int]
     L.akz_context_enable_timing.argtypes = [vp, C.c_int]
     L.akz_context_stage_times.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]
     L.akz_extract_u8.argtypes = [vp, vp, C.c_uint32, C.c_uint32, C.c_size_t, C.POINTER(Config), C.POINTER(vp)]
@@ -312,6 +313,10 @@ class Engine:
     def set_sub_batch(self, images):
         """Images per pipeline sub-batch (akz_context_set_sub_batch)."""
         _check(lib().akz_context_set_sub_batch(self._h, int(images)))
+
+    def set_match_path(self, path):
+        """"auto" | "popc" | "tensor" (akz_context_set_match_path)."""
+        _check(lib().akz_context_set_match_path(self._h, {"auto": 0, "popc": 1, "tensor": 2}[path]))
 
     def enable_timing(self, on=True):
         _check(lib().akz_context_enable_timing(self._h, int(on)))

@@ -10,7 +10,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libakaze_b200.so")
-SOURCES = ["akaze_api.cu", "scale_space.cu", "detector.cu", "keypoints.cu", "matcher.cu"]
+SOURCES = ["akaze_api.cu", "scale_space.cu", "detector.cu", "keypoints.cu", "matcher.cu", "matcher_tc.cu"]
 HEADERS = ["common.cuh", os.path.join("..", "..", "include", "akaze_b200.h")]
 
 NVCC_FLAGS = [

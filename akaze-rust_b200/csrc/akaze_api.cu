@@ -113,7 +113,7 @@ std::string build_plan(uint32_t w, uint32_t h, const akz_config& cfg, Plan* P) {
         const int s0 = (int)ceilf(pf * 1.0f), s1 = (int)ceilf(pf * (2.0f / 3.0f)), s2 = (int)ceilf(pf * (1.0f / 2.0f));
         const int n0 = (2 * p + s0 - 1) / s0, n1 = (2 * p + s1 - 1) / s1, n2 = (2 * p + s2 - 1) / s2;
         if (n0 != 2 || n1 != 3 || n2 != 4) return "descriptor_pattern_size does not give the 2x2/3x3/4x4 MLDB grids";
-        if (4 * s0 * s0 > 448 || 9 * s1 * s1 > 448 || 16 * s2 * s2 > 448) return "descriptor_pattern_size too large (max 10)";
+        if (2 * s0 > 21 || 3 * s1 > 21 || 4 * s2 > 21) return "descriptor_pattern_size too large (max 10)";  // kDescM lattice of k_descriptor
     }
     P->w = w;
     P->h = h;
@@ -354,6 +354,10 @@ struct akz_context {
     void* m_parts = nullptr;
     void* m_out = nullptr;
     size_t m_q_cap = 0, m_db_cap = 0, m_parts_cap = 0, m_out_cap = 0;
+    void* m_qimg = nullptr;   // int8 operand images of the tensor-core matcher (matcher_tc.cu)
+    void* m_dbimg = nullptr;
+    size_t m_qimg_cap = 0, m_dbimg_cap = 0;
+    int match_path = AKZ_MATCH_AUTO;
 };
 
 struct akz_features {
@@ -806,6 +810,7 @@ int akz_create(int device, uint32_t max_width, uint32_t max_height, uint32_t max
     CK(cudaStreamCreateWithFlags(&c->stream_d2h, cudaStreamNonBlocking));
     CK(init_detector_attributes());
     CK(init_keypoint_attributes());
+    CK(init_matcher_tc_attributes());
     *out = c.release();
     return AKZ_OK;
 }
@@ -832,6 +837,8 @@ void akz_destroy(akz_context* c) {
     cudaFree(c->m_db);
     cudaFree(c->m_parts);
     cudaFree(c->m_out);
+    cudaFree(c->m_qimg);
+    cudaFree(c->m_dbimg);
     for (auto& e : c->ev_pool) {
         cudaEventDestroy(e.first);
         cudaEventDestroy(e.second);
@@ -872,6 +879,12 @@ int akz_context_set_limits(akz_context* c, uint32_t max_candidates, uint32_t max
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->stream_kp);
     free_buffers(c);
+    return AKZ_OK;
+}
+
+int akz_context_set_match_path(akz_context* c, int path) {
+    if (!c || path < AKZ_MATCH_AUTO || path > AKZ_MATCH_TENSOR) return fail(AKZ_ERR_INVALID, "bad match path");
+    c->match_path = path;
     return AKZ_OK;
 }
 
@@ -1017,15 +1030,26 @@ int akz_match_top2_device(akz_context* c, const void* d_q, uint64_t nq, const vo
     if (nq == 0) return AKZ_OK;
     if (ndb > 0xffffffffull || nq > 0xffffffffull) return fail(AKZ_ERR_CAPACITY, "more than 2^32 descriptors");
     CK(cudaSetDevice(c->device));
-    const int parts = match_parts(nq, ndb);
-    if (parts == 1) {
-        c->launches += launch_match_top2(c->stream, (const uint8_t*)d_q, nq, (const uint8_t*)d_db, ndb, db_index_base, (akz_top2*)d_out, 1);
-    } else {
+    // tensor-core path (matcher_tc.cu) unless the problem is too small to amortise the 64 KB operand tiles
+    const bool tensor = ndb > 0 && (c->match_path == AKZ_MATCH_TENSOR || (c->match_path == AKZ_MATCH_AUTO && nq * ndb >= (1ull << 20)));
+    const int parts = tensor ? match_tc_parts(nq, ndb) : match_parts(nq, ndb);
+    akz_top2* dst = (akz_top2*)d_out;
+    if (parts > 1) {
         int rc = grow(&c->m_parts, &c->m_parts_cap, (size_t)parts * nq * sizeof(akz_top2));
         if (rc != AKZ_OK) return rc;
-        c->launches += launch_match_top2(c->stream, (const uint8_t*)d_q, nq, (const uint8_t*)d_db, ndb, db_index_base, (akz_top2*)c->m_parts, parts);
-        c->launches += launch_merge_top2(c->stream, (const akz_top2*)c->m_parts, (uint32_t)parts, nq, (akz_top2*)d_out);
+        dst = (akz_top2*)c->m_parts;
     }
+    if (tensor) {
+        int rc = grow(&c->m_qimg, &c->m_qimg_cap, match_tc_query_image_bytes(nq));
+        if (rc != AKZ_OK) return rc;
+        rc = grow(&c->m_dbimg, &c->m_dbimg_cap, match_tc_db_image_bytes(ndb));
+        if (rc != AKZ_OK) return rc;
+        c->launches += launch_match_tc(c->stream, (const uint8_t*)d_q, nq, (const uint8_t*)d_db, ndb, db_index_base, (uint8_t*)c->m_qimg,
+                                       (uint8_t*)c->m_dbimg, dst, parts);
+    } else {
+        c->launches += launch_match_top2(c->stream, (const uint8_t*)d_q, nq, (const uint8_t*)d_db, ndb, db_index_base, dst, parts);
+    }
+    if (parts > 1) c->launches += launch_merge_top2(c->stream, (const akz_top2*)c->m_parts, (uint32_t)parts, nq, (akz_top2*)d_out);
     CK(cudaGetLastError());
     return AKZ_OK;
 }

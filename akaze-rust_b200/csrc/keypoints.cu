@@ -586,23 +586,61 @@ k_orientation(const PlanDev* __restrict__ plan, const float* __restrict__ lx_pla
 }
 
 // ------------------------------------------------------------------------------------------------
-// K6: MLDB descriptor, one warp per keypoint (descriptors.rs:37-175), in two phases per grid level:
-//   1. all 32 lanes evaluate the level's samples (400 / 441 / 400 of them: rotated position, rounded
-//      gather of Lt, Lx, Ly, rotated derivative) into shared memory, in (cell, k, l) order;
-//   2. one lane per (cell, channel) adds that cell's samples SEQUENTIALLY from shared memory (k outer,
-//      l inner, f32, exactly the reference's summation order) and divides by the sample count.
-// Comparisons are packed LSB-first: grid level, then channel, then pairs i<j.
+// K6: MLDB descriptor, one warp per keypoint (descriptors.rs:37-175).
+//
+// The three grids of the reference (2x2 cells of p x p samples, 3x3 of ceil(2p/3)^2, 4x4 of ceil(p/2)^2)
+// all sample the SAME lattice: sample (k, l) sits at the rotated offset ((l+0.5), (k+0.5)) * scale whatever
+// the grid, with k, l in [-p, -p + M), M = max over grids of cells*step (21 for p = 10). So
+//   1. the warp evaluates the M x M lattice once (rotated position, rounded gather of Lt, Lx, Ly, rotated
+//      derivative) into shared memory -- 441 gathers instead of the reference's 1241. Adjacent lanes take
+//      adjacent lattice points along the lattice axis that is closer to the image x axis (k if |cos| >=
+//      |sin|, else l), so that one warp-wide gather touches few cache lines;
+//   2. one lane per (cell, channel) adds that cell's samples SEQUENTIALLY from shared memory (k outer, l
+//      inner, f32: exactly the reference's summation order) and divides by the sample count;
+//   3. the comparisons are bit-packed with warp ballots through a (value i, value j) table per bit
+//      (LSB-first: grid level, then channel, then pairs i<j, descriptors.rs:161-173).
 // ------------------------------------------------------------------------------------------------
 constexpr int kDescWarps = 8;
-constexpr int kDescMaxSamples = 448;  // 441 for the 3x3 grid of 7x7 cells (pattern 10)
+constexpr int kDescM = 21;          // lattice edge for pattern 10 (3 cells x 7)
+constexpr int kDescCS = 463;        // channel stride in shared memory (>= 21*21; chosen for few bank conflicts in phase 2)
+constexpr int kDescBits = 486;      // (6 + 36 + 120) * 3
+
+// sums of one grid level: NC x NC cells of STEP x STEP lattice points, lane t owns (cell, channel) = (t / nch, t % nch)
+template <int STEP, int NC>
+__device__ __forceinline__ void desc_cell_sums(const float* smp, float* val, int M, int nch, int lane) {
+    for (int t = lane; t < NC * NC * nch; t += 32) {
+        const int c = t / nch, ch = t - c * nch;
+        const int ci = c / NC, cj = c - ci * NC;
+        const float* v = smp + ch * kDescCS + (ci * STEP) * M + cj * STEP;
+        float acc = 0.0f;
+#pragma unroll 2
+        for (int kk = 0; kk < STEP; kk++) {
+#pragma unroll
+            for (int ll = 0; ll < STEP; ll++) acc = acc + v[kk * M + ll];
+        }
+        val[c * 3 + ch] = acc / (float)(STEP * STEP);
+    }
+}
+__device__ __forceinline__ void desc_cell_sums_rt(const float* smp, float* val, int M, int nch, int lane, int step, int nc) {
+    const float ns = (float)(step * step);
+    for (int t = lane; t < nc * nc * nch; t += 32) {
+        const int c = t / nch, ch = t - c * nch;
+        const int ci = c / nc, cj = c - ci * nc;
+        const float* v = smp + ch * kDescCS + (ci * step) * M + cj * step;
+        float acc = 0.0f;
+        for (int kk = 0; kk < step; kk++)
+            for (int ll = 0; ll < step; ll++) acc = acc + v[kk * M + ll];
+        val[c * 3 + ch] = acc / ns;
+    }
+}
 
 __global__ void __launch_bounds__(32 * kDescWarps)
 k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plane, const float* __restrict__ lx_plane,
              const float* __restrict__ ly_plane, int batch, unsigned int kp_cap, const akz_keypoint* __restrict__ kps,
              const unsigned int* __restrict__ n_kp, uint8_t* __restrict__ desc, unsigned int* __restrict__ err_flags) {
-    __shared__ float s_smp[kDescWarps][3][kDescMaxSamples];
-    __shared__ float s_val[kDescWarps][29 * 3];
-    __shared__ unsigned int s_bits[kDescWarps][16];
+    __shared__ float s_smp[kDescWarps][3 * kDescCS];
+    __shared__ float s_val[kDescWarps][29 * 3 + 1];
+    __shared__ unsigned short s_cmp[512];  // per descriptor bit: (index of value i) | (index of value j) << 8
     const int img = blockIdx.y;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned int n = min(n_kp[img], kp_cap);
@@ -611,112 +649,107 @@ k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plan
     const int pattern = plan->pattern_size;
     // sample_size per grid level: ceil(pattern * {1, 2/3, 1/2}) in f32 (descriptors.rs:50,61)
     const float pf = (float)pattern;
-    const int steps[3] = {(int)ceilf(pf * 1.0f), (int)ceilf(pf * (2.0f / 3.0f)), (int)ceilf(pf * (1.0f / 2.0f))};
+    const int st0 = (int)ceilf(pf * 1.0f), st1 = (int)ceilf(pf * (2.0f / 3.0f)), st2 = (int)ceilf(pf * (1.0f / 2.0f));
+    const int M = max(2 * st0, max(3 * st1, 4 * st2));  // <= kDescM (validated on the host)
+    const int MM = M * M;
+    const int nbits = 162 * nch;
+    {   // bit -> (i, j) table, identical for every keypoint
+        for (int d = threadIdx.x; d < 512; d += blockDim.x) {
+            unsigned short e = 0;
+            if (d < nbits) {
+                int rem = d, cell_base = 0, g = 0;
+                for (; g < 3; g++) {
+                    const int cnt = (g + 2) * (g + 2), pairs = cnt * (cnt - 1) / 2;
+                    if (rem < nch * pairs) break;
+                    rem -= nch * pairs;
+                    cell_base += cnt;
+                }
+                const int cnt = (g + 2) * (g + 2), pairs = cnt * (cnt - 1) / 2;
+                const int pos = rem / pairs;
+                int pidx = rem - pos * pairs, i = 0;
+                while (pidx >= cnt - 1 - i) {  // unrank pidx -> (i, j), i < j, row-major over i
+                    pidx -= cnt - 1 - i;
+                    i++;
+                }
+                const int j = i + 1 + pidx;
+                e = (unsigned short)(((cell_base + i) * 3 + pos) | (((cell_base + j) * 3 + pos) << 8));
+            }
+            s_cmp[d] = e;
+        }
+    }
+    __syncthreads();
+    float* smp = s_smp[wib];
+    float* val = s_val[wib];
     for (unsigned int kidx = blockIdx.x * (blockDim.x >> 5) + wib; kidx < n; kidx += warps) {
         const akz_keypoint kp = kps[(size_t)img * kp_cap + kidx];
         const LevelDev& lv = plan->lv[kp.class_id];
         const float ratio = lv.ratio;
         const float scale = lv.s_smp;
+        const int W = lv.w, H = lv.h;
         const float xf = kp.x / ratio, yf = kp.y / ratio;
         const float co = (float)cos((double)kp.angle), si = (float)sin((double)kp.angle);
-        const float* Lt = lt_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
-        const float* Lx = lx_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
-        const float* Ly = ly_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
+        const size_t base = (size_t)lv.off * batch + (size_t)img * W * H;
+        const float* Lt = lt_plane + base;
+        const float* Lx = lx_plane + base;
+        const float* Ly = ly_plane + base;
         bool oob = false;
-        if (lane < 16) s_bits[wib][lane] = 0;
-        int cell_base = 0, dpos_base = 0;
-#pragma unroll 1
-        for (int g = 0; g < 3; g++) {
-            const int step = steps[g];
-            const int nc = g + 2;                 // cells per axis (validated on the host: 2, 3, 4)
-            const int per_cell = step * step;
-            const int total = nc * nc * per_cell;  // <= kDescMaxSamples (validated on the host)
-            // ---- phase 1: lane owns a contiguous chunk of samples; s = cell*per_cell + kk*step + ll
-            const int chunk = (total + 31) / 32;
-            int sidx = lane * chunk;
-            const int send = min(total, sidx + chunk);
-            int cell = sidx / per_cell;
-            int rem = sidx - cell * per_cell;
-            int kk = rem / step, ll = rem - kk * step;
-            int ci = cell / nc, cj = cell - ci * nc;
-            for (; sidx < send; sidx++) {
-                const int k = -pattern + ci * step + kk, l = -pattern + cj * step + ll;
-                const float lf = (float)l + 0.5f, kf = (float)k + 0.5f;
+        // ---- phase 1: the M x M lattice; fast lane index runs along the lattice axis closest to image x
+        const bool k_fast = fabsf(co) >= fabsf(si);
+        for (int s0 = 0; s0 < MM; s0 += 32) {
+            const int s = s0 + lane;
+            if (s < MM) {
+                const int a = s / M, b = s - a * M;
+                const int kk = k_fast ? b : a, ll = k_fast ? a : b;
+                const float lf = (float)(ll - pattern) + 0.5f, kf = (float)(kk - pattern) + 0.5f;
                 const float sample_y = yf + (lf * co * scale + kf * si * scale);
                 const float sample_x = xf + (-lf * si * scale + kf * co * scale);
                 int y1 = (int)roundf(sample_y), x1 = (int)roundf(sample_x);
-                if (x1 < 0 || y1 < 0 || x1 >= lv.w || y1 >= lv.h) {
+                if (x1 < 0 || y1 < 0 || x1 >= W || y1 >= H) {
                     oob = true;
-                    x1 = min(max(x1, 0), lv.w - 1);
-                    y1 = min(max(y1, 0), lv.h - 1);
+                    x1 = min(max(x1, 0), W - 1);
+                    y1 = min(max(y1, 0), H - 1);
                 }
-                const size_t at = (size_t)y1 * lv.w + x1;
-                s_smp[wib][0][sidx] = Lt[at];
+                const size_t at = (size_t)y1 * W + x1;
+                const int so = kk * M + ll;
+                smp[so] = Lt[at];
                 if (nch > 1) {
                     const float rx = Lx[at], ry = Ly[at];
                     if (nch == 2) {
-                        s_smp[wib][1][sidx] = sqrtf(rx * rx + ry * ry);
+                        smp[kDescCS + so] = sqrtf(rx * rx + ry * ry);
                     } else {
                         const float rry = rx * co + ry * si;
                         const float rrx = -rx * si + ry * co;
-                        s_smp[wib][1][sidx] = rrx;
-                        s_smp[wib][2][sidx] = rry;
-                    }
-                }
-                if (++ll == step) {
-                    ll = 0;
-                    if (++kk == step) {
-                        kk = 0;
-                        cell++;
-                        if (++cj == nc) {
-                            cj = 0;
-                            ci++;
-                        }
+                        smp[kDescCS + so] = rrx;
+                        smp[2 * kDescCS + so] = rry;
                     }
                 }
             }
-            __syncwarp();
-            // ---- phase 2: sequential sums per (cell, channel)
-            const float ns = (float)per_cell;
-            for (int t = lane; t < nc * nc * nch; t += 32) {
-                const int c = t / nch, ch = t - c * nch;
-                const float* v = &s_smp[wib][ch][c * per_cell];
-                float acc = 0.0f;
-                for (int r = 0; r < per_cell; r++) acc = acc + v[r];
-                s_val[wib][(cell_base + c) * 3 + ch] = acc / ns;
-            }
-            __syncwarp();
-            cell_base += nc * nc;
-        }
-        // comparisons: bit position = dpos (descriptors.rs:161-173)
-        cell_base = 0;
-        for (int g = 0; g < 3; g++) {
-            const int cnt = (g + 2) * (g + 2);
-            const int pairs = cnt * (cnt - 1) / 2;
-            for (int pos = 0; pos < nch; pos++) {
-                for (int pidx = lane; pidx < pairs; pidx += 32) {
-                    // unrank pidx -> (i,j), i<j, row-major over i
-                    int i = 0, rem = pidx;
-                    while (rem >= cnt - 1 - i) {
-                        rem -= cnt - 1 - i;
-                        i++;
-                    }
-                    const int j = i + 1 + rem;
-                    const float vi = s_val[wib][(cell_base + i) * 3 + pos];
-                    const float vj = s_val[wib][(cell_base + j) * 3 + pos];
-                    if (vi > vj) {
-                        const int dpos = dpos_base + pos * pairs + pidx;
-                        atomicOr(&s_bits[wib][dpos >> 5], 1u << (dpos & 31));
-                    }
-                }
-            }
-            dpos_base += nch * pairs;
-            cell_base += cnt;
         }
         __syncwarp();
+        // ---- phase 2: sequential sums per (cell, channel); values of grid g start at cell_base(g) = 0, 4, 13
+        if (pattern == 10) {
+            desc_cell_sums<10, 2>(smp, val, M, nch, lane);
+            desc_cell_sums<7, 3>(smp, val + 4 * 3, M, nch, lane);
+            desc_cell_sums<5, 4>(smp, val + 13 * 3, M, nch, lane);
+        } else {
+            desc_cell_sums_rt(smp, val, M, nch, lane, st0, 2);
+            desc_cell_sums_rt(smp, val + 4 * 3, M, nch, lane, st1, 3);
+            desc_cell_sums_rt(smp, val + 13 * 3, M, nch, lane, st2, 4);
+        }
+        __syncwarp();
+        // ---- phase 3: bit d of the descriptor = values[i] > values[j]; word w is the ballot of bits 32w..32w+31
+        unsigned int my_word = 0;
+#pragma unroll
+        for (int w = 0; w < 16; w++) {
+            const int d = w * 32 + lane;
+            const unsigned int e = s_cmp[d];
+            const bool bit = d < nbits && val[e & 255u] > val[e >> 8];
+            const unsigned int word = __ballot_sync(0xffffffffu, bit);
+            if (lane == w) my_word = word;
+        }
         if (lane < 16) {
             unsigned int* out = (unsigned int*)(desc + ((size_t)img * kp_cap + kidx) * kDescStride);
-            out[lane] = s_bits[wib][lane];
+            out[lane] = my_word;
         }
         if (oob) atomicOr(&err_flags[img], (unsigned int)kErrBounds);
         __syncwarp();

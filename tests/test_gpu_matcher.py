@@ -20,14 +20,23 @@ def make(nq, ndb, seed, width=64):
     return q, db
 
 
+@pytest.fixture(params=["popc", "tensor"])
+def path_engine(engine, request):
+    """The session engine forced onto one matcher kernel: integer popc (matcher.cu) or tcgen05 int8 (matcher_tc.cu)."""
+    engine.set_match_path(request.param)
+    yield engine
+    engine.set_match_path("auto")
+
+
 def assert_same(t, o):
     bi, b, s = o
     assert np.array_equal(t["best"], b) and np.array_equal(t["second"], s) and np.array_equal(t["best_idx"], bi)
 
 
 @pytest.mark.parametrize("nq,ndb", [(1, 1), (1, 0), (3, 2), (31, 33), (512, 128), (513, 129), (300, 1000),
-                                     (2000, 5000), (64, 70000), (7395, 5629)])
-def test_top2_exact(engine, oracle, nq, ndb):
+                                     (2000, 5000), (64, 70000), (7395, 5629), (257, 127), (255, 1025), (128, 128)])
+def test_top2_exact(path_engine, oracle, nq, ndb):
+    engine = path_engine
     q, db = make(nq, ndb, nq * 7919 + ndb)
     k = min(nq, ndb) // 3
     if k:
@@ -36,7 +45,8 @@ def test_top2_exact(engine, oracle, nq, ndb):
     assert_same(engine.match_top2(q, db, desc_len=61), oracle.match_top2(q, db, desc_len=61))
 
 
-def test_unpadded_rows_and_desc_len(engine, oracle):
+def test_unpadded_rows_and_desc_len(path_engine, oracle):
+    engine = path_engine
     q, db = make(200, 333, 5, width=61)  # rows exactly as Descriptor.vector (61 bytes, descriptors.rs:45)
     assert_same(engine.match_top2(q, db), oracle.match_top2(q, db))
     q, db = make(100, 100, 6)
@@ -44,7 +54,20 @@ def test_unpadded_rows_and_desc_len(engine, oracle):
     assert_same(engine.match_top2(q, db, desc_len=32), oracle.match_top2(q, db, desc_len=32))
 
 
-def test_all_equal_and_far(engine, oracle):
+def test_full_width_rows(path_engine, oracle):
+    """All 512 bits of a 64-byte row in use (desc_len = 64): no spare bits for either kernel to rely on."""
+    engine = path_engine
+    rng = np.random.default_rng(77)
+    q = rng.integers(0, 256, (300, 64), dtype=np.uint8)
+    db = rng.integers(0, 256, (900, 64), dtype=np.uint8)
+    db[5] = q[7]
+    db[600] = q[7]
+    db[100] = ~q[9]
+    assert_same(engine.match_top2(q, db, desc_len=64), oracle.match_top2(q, db, desc_len=64))
+
+
+def test_all_equal_and_far(path_engine, oracle):
+    engine = path_engine
     q = np.zeros((50, 64), np.uint8)
     db = np.zeros((70, 64), np.uint8)
     t = engine.match_top2(q, db, desc_len=61)
@@ -56,7 +79,8 @@ def test_all_equal_and_far(engine, oracle):
     assert np.all(t["best"] == 486) and np.all(t["second"] == 486) and np.all(t["best_idx"] == 0)
 
 
-def test_descriptor_match_lowe(engine, oracle):
+def test_descriptor_match_lowe(path_engine, oracle):
+    engine = path_engine
     q, db = make(500, 800, 9)
     for i in range(0, 500, 5):                  # plant near matches so that the Lowe test passes sometimes
         db[(i * 7) % 800] = q[i]
@@ -70,9 +94,10 @@ def _dev(a):
     return torch.from_numpy(a).cuda()
 
 
-def test_sharded_device_path_matches_unsharded(engine, oracle, akz):
+def test_sharded_device_path_matches_unsharded(path_engine, oracle, akz):
     """Database sharded contiguously, per-shard top-2 with db_index_base, merged by the CUDA merge kernel
     (what each rank does after the NCCL all-gather)."""
+    engine = path_engine
     q, db = make(700, 4099, 31)
     db[4000] = q[0]
     db[17] = q[0]
