@@ -14,6 +14,9 @@
 // exact +0 and are skipped. Every pass clamps like fill_border (see scale_space.cu). Candidates are
 // written as one bit per pixel; a second set of kernels turns the bitmask into a list in raster order,
 // which the order-dependent cache pass of the reference needs.
+#include <algorithm>
+#include <cstdlib>
+
 #include "common.cuh"
 #include "tile_util.cuh"
 
@@ -358,6 +361,220 @@ k_detector_fast(const float* __restrict__ lsmooth, size_t img_px, float* __restr
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Streaming path (default): one warp owns a strip of 128 columns (4 adjacent columns per lane, float4
+// I/O) and marches down the rows, like k_fed. The whole derivative chain is a software pipeline in the
+// row index: when Lsmooth row c arrives,
+//   A, Bo (row c)            <- H taps of Lsmooth row c (neighbour lanes by shuffle)
+//   Lx, Ly (row c-S)         <- V taps of A / Bo rows c-2S, c-S, c
+//   C, E, D (row c-S)        <- H taps of that Lx / Ly row
+//   Lxx, Lxy, Lyy, Ldet (row c-2S) <- V taps of C / E / D rows c-3S, c-2S, c-S
+//   candidates (row c-2S-1)  <- Ldet rows c-2S-2 .. c-2S kept in registers
+// The rows a V tap needs again later live in per-lane ring buffers in shared memory (each lane reads
+// back only what it wrote itself: no barriers at all); nothing is recomputed vertically inside a
+// segment, and the shared-memory traffic is 13 128-bit accesses per 4 pixels instead of ~45 in the
+// tile kernel, which ncu shows to be shared-memory bound (profiles/r1f). fill_border: every pass of
+// the reference clamps with the same half-width S, so rows < S / > H-1-S of every intermediate equal
+// rows S / H-1-S: ring reads clamp their row index, rows beyond H-1-S reuse the registers of row
+// H-1-S, and border rows are written when the row they replicate is produced. Columns: the H-pass
+// outputs of columns < S / > W-1-S are replaced by those of columns S / W-1-S (one shuffle per array,
+// only in strips that touch the image border); V passes inherit it.
+// ------------------------------------------------------------------------------------------------
+constexpr int DS_W = 128;
+template <int S>
+struct StreamGeo {
+    static constexpr int HX = ((2 * S + 1) + 3) & ~3;  // x halo: Ldet is needed one column beyond the strip's outputs
+    static constexpr int UX = DS_W - 2 * HX;           // output columns per strip
+    static constexpr int D = (S == 2) ? 4 : 8;         // ring depth: power of two >= 2S
+};
+
+// ext[0..3] = left lane's v, ext[4..7] = v, ext[8..11] = right lane's v (only what a +-S tap touches is fetched)
+template <int S>
+__device__ __forceinline__ void h_neighbours(const float (&v)[4], float (&ext)[12]) {
+#pragma unroll
+    for (int j = 0; j < 12; j++) ext[j] = 0.0f;
+#pragma unroll
+    for (int j = 0; j < 4; j++) ext[4 + j] = v[j];
+#pragma unroll
+    for (int j = 4 - S; j < 4; j++) ext[j] = __shfl_up_sync(0xffffffffu, v[j], 1);
+#pragma unroll
+    for (int j = 0; j < S; j++) ext[8 + j] = __shfl_down_sync(0xffffffffu, v[j], 1);
+}
+
+template <int S>
+__global__ void __launch_bounds__(32)
+k_detector_stream(const float* __restrict__ lsmooth, size_t img_px, float* __restrict__ oLx, float* __restrict__ oLy,
+                  float* __restrict__ oLdet, unsigned int* __restrict__ mask, size_t mask_img_words, DetParams p, int strips_x,
+                  int n_seg, int RL) {
+    using G = StreamGeo<S>;
+    constexpr unsigned int FULL = 0xffffffffu;
+    constexpr int M = G::D - 1;
+    __shared__ float4 ring[5][G::D][32];  // A, Bo, C, E, D
+    const int lane = threadIdx.x;
+    const int si = blockIdx.x % strips_x, sj = blockIdx.x / strips_x;
+    const int img = blockIdx.z;
+    const int W = p.W, H = p.H;
+    const float n = p.n, wn = p.wn;
+    const int xb = si * G::UX - G::HX;  // first column of the strip (multiple of 4, may be negative)
+    const int x0 = xb + 4 * lane;
+    const int Ya = sj * RL, Yb = (sj == n_seg - 1) ? H : Ya + RL;
+    const bool xin = x0 >= 0 && x0 < W;
+    const bool xout = xin && x0 >= si * G::UX && x0 < (si + 1) * G::UX;
+    const int ylo = S, yhi = H - 1 - S;  // rows every pass computes; the others replicate them
+    const int c_begin = max(ylo, Ya - 1 - 2 * S), c_end = Yb + 2 * S;
+    const bool has_l = xb < S, has_r = xb + DS_W - 1 > W - 1 - S;
+    const int lane_l = (S - xb) >> 2;          // lane holding column S (component S & 3)
+    const int lane_r = (W - 1 - S - xb) >> 2;  // lane holding column W-1-S (component (3 - S) & 3: W % 4 == 0)
+    bool fl[4], fr[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        fl[j] = x0 + j < S;
+        fr[j] = x0 + j > W - 1 - S;
+    }
+    const size_t ibase = (size_t)img * img_px;
+    const float* L = lsmooth + ibase;
+    float* ox = oLx + ibase;
+    float* oy = oLy + ibase;
+    float* od = oLdet + ibase;
+    unsigned int* m = mask + (size_t)img * mask_img_words;
+
+    auto load_row = [&](int c) {
+        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (xin && c <= yhi) v = ld4(L + (size_t)c * W + x0);
+        return v;
+    };
+    auto fix_cols = [&](float(&v)[4]) {  // fill_border in x of an H-pass output
+        if (has_l) {
+            const float t = __shfl_sync(FULL, v[S & 3], lane_l);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (fl[j]) v[j] = t;
+        }
+        if (has_r) {
+            const float t = __shfl_sync(FULL, v[(3 - S) & 3], lane_r & 31);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (fr[j]) v[j] = t;
+        }
+    };
+    // row o of an output plane plus the border rows that replicate it (fill_border in y)
+    auto store_rows = [&](float* plane, int o, const float(&v)[4]) {
+        if (!xout) return;
+        const float4 q = make_float4(v[0], v[1], v[2], v[3]);
+        if (o >= Ya && o < Yb) st4(plane + (size_t)o * W + x0, q);
+        if (o == ylo)
+            for (int r = max(0, Ya); r < min(ylo, Yb); r++) st4(plane + (size_t)r * W + x0, q);
+        if (o == yhi)
+            for (int r = max(yhi + 1, Ya); r < min(H, Yb); r++) st4(plane + (size_t)r * W + x0, q);
+    };
+    auto clamp_lo = [&](int r) { return r < ylo ? ylo : r; };
+
+    float a[4], bo[4], lx[4], ly[4], cc[4], ee[4], dd[4], det_m[4], det_0[4], det_p[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) a[j] = bo[j] = lx[j] = ly[j] = cc[j] = ee[j] = dd[j] = det_m[j] = det_0[j] = det_p[j] = 0.0f;
+    float4 Lc = load_row(c_begin), Ln1 = load_row(c_begin + 1), Ln2 = load_row(c_begin + 2);
+
+    for (int c = c_begin; c <= c_end; c++) {
+        const float4 Ln3 = load_row(c + 3);
+        // ---- A = H_main(Lsmooth), Bo = H_off(Lsmooth), row c (rows beyond yhi keep the registers of row yhi)
+        if (c <= yhi) {
+            const float v[4] = {Lc.x, Lc.y, Lc.z, Lc.w};
+            float e[12];
+            h_neighbours<S>(v, e);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                a[j] = (n * e[4 + j - S] + wn * e[4 + j]) + n * e[4 + j + S];
+                bo[j] = e[4 + j + S] - e[4 + j - S];
+            }
+            fix_cols(a);
+            fix_cols(bo);
+        }
+        // ---- Lx = V_off(A), Ly = V_main(Bo), row o1 = c - S
+        const int o1 = c - S;
+        const bool row1 = o1 >= ylo && o1 <= yhi;
+        if (row1) {
+            const int rm = clamp_lo(o1 - S) & M;
+            const float4 a_m = ring[0][rm][lane], b_m = ring[1][rm][lane], b_0 = ring[1][o1 & M][lane];
+            lx[0] = a[0] - a_m.x; lx[1] = a[1] - a_m.y; lx[2] = a[2] - a_m.z; lx[3] = a[3] - a_m.w;
+            ly[0] = (n * b_m.x + wn * b_0.x) + n * bo[0];
+            ly[1] = (n * b_m.y + wn * b_0.y) + n * bo[1];
+            ly[2] = (n * b_m.z + wn * b_0.z) + n * bo[2];
+            ly[3] = (n * b_m.w + wn * b_0.w) + n * bo[3];
+            store_rows(ox, o1, lx);
+            store_rows(oy, o1, ly);
+        }
+        if (c <= yhi) {  // after the reads above: row c may reuse the slot of row c - 2S
+            ring[0][c & M][lane] = make_float4(a[0], a[1], a[2], a[3]);
+            ring[1][c & M][lane] = make_float4(bo[0], bo[1], bo[2], bo[3]);
+        }
+        // ---- C = H_main(Lx), E = H_off(Lx), D = H_off(Ly), row o1
+        if (row1) {
+            float e[12];
+            h_neighbours<S>(lx, e);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                cc[j] = (n * e[4 + j - S] + wn * e[4 + j]) + n * e[4 + j + S];
+                ee[j] = e[4 + j + S] - e[4 + j - S];
+            }
+            h_neighbours<S>(ly, e);
+#pragma unroll
+            for (int j = 0; j < 4; j++) dd[j] = e[4 + j + S] - e[4 + j - S];
+            fix_cols(cc);
+            fix_cols(ee);
+            fix_cols(dd);
+        }
+        // ---- Lxx = V_off(C), Lxy = V_main(E), Lyy = V_main(D), Ldet, row o2 = c - 2S
+        const int o2 = o1 - S;
+        if (o2 >= ylo && o2 <= yhi) {
+            const int rm = clamp_lo(o2 - S) & M;
+            const float4 c_m = ring[2][rm][lane], e_m = ring[3][rm][lane], e_0 = ring[3][o2 & M][lane];
+            const float4 d_m = ring[4][rm][lane], d_0 = ring[4][o2 & M][lane];
+            const float cm[4] = {c_m.x, c_m.y, c_m.z, c_m.w}, em[4] = {e_m.x, e_m.y, e_m.z, e_m.w}, e0[4] = {e_0.x, e_0.y, e_0.z, e_0.w};
+            const float dm[4] = {d_m.x, d_m.y, d_m.z, d_m.w}, d0[4] = {d_0.x, d_0.y, d_0.z, d_0.w};
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float lxx = cc[j] - cm[j];
+                const float lyy = (n * dm[j] + wn * d0[j]) + n * dd[j];
+                const float lxy = (n * em[j] + wn * e0[j]) + n * ee[j];
+                det_m[j] = det_0[j];
+                det_0[j] = det_p[j];
+                det_p[j] = ((lxx * lyy) - (lxy * lxy)) * p.quat;  // detector_response.rs:52
+            }
+            store_rows(od, o2, det_p);
+        } else if (o2 > yhi) {  // Ldet(o2) = Ldet(yhi)
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                det_m[j] = det_0[j];
+                det_0[j] = det_p[j];
+            }
+        }
+        if (row1) {
+            ring[2][o1 & M][lane] = make_float4(cc[0], cc[1], cc[2], cc[3]);
+            ring[3][o1 & M][lane] = make_float4(ee[0], ee[1], ee[2], ee[3]);
+            ring[4][o1 & M][lane] = make_float4(dd[0], dd[1], dd[2], dd[3]);
+        }
+        // ---- candidates of row o3 = o2 - 1: threshold + strict 4-neighbour maximum + is_out
+        const int o3 = o2 - 1;
+        if (o3 >= Ya && o3 < Yb && o3 >= p.ymin && o3 <= p.ymax) {
+            const float left = __shfl_up_sync(FULL, det_0[3], 1), right = __shfl_down_sync(FULL, det_0[0], 1);
+            unsigned int nib = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int x = x0 + j;
+                const float v = det_0[j];
+                const float l = j > 0 ? det_0[j > 0 ? j - 1 : 0] : left;
+                const float r = j < 3 ? det_0[j < 3 ? j + 1 : 3] : right;
+                const bool cand = xout && x >= p.xmin && x <= p.xmax && v > p.thr && v > r && v > l && v > det_m[j] && v > det_p[j];
+                nib |= (cand ? 1u : 0u) << j;
+            }
+            if (nib) atomicOr(&m[(size_t)o3 * p.wpr + (x0 >> 5)], nib << (x0 & 31));
+        }
+        Lc = Ln1;
+        Ln1 = Ln2;
+        Ln2 = Ln3;
+    }
+}
+
 // ---- bitmask -> ordered list ------------------------------------------------------------------
 // rows are enumerated level-major; one warp per row
 __device__ __forceinline__ int find_level(const PlanDev* plan, int grow, int* row_in_level) {
@@ -511,6 +728,27 @@ int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level)
     // level 0: Lsmooth is Lt (lib.rs:58)
     const float* ls = (level == 0) ? B.Lt : (B.keep ? B.Lsmooth + off : B.Lsmooth);
     unsigned int* mk = B.mask + lv.mask_off;
+    // streaming kernel: additionally needs the candidate rows (and their two neighbours) to be rows the passes compute
+    static const bool force_tile = getenv("AKZ_DETECTOR_TILE") != nullptr;  // A/B switch for profiling
+    const bool stream = fast && !force_tile && lv.ymin >= lv.s_det + 1 && lv.ymax <= lv.h - 2 - lv.s_det && lv.h >= 4 * lv.s_det + 4;
+    if (stream) {
+        const int RL = lv.h >= 512 ? 128 : (lv.h >= 256 ? 64 : 32);
+        const int n_seg = std::max(1, (lv.h - 1 - lv.s_det) / RL);
+        float* px = B.Lx + off;
+        float* py = B.Ly + off;
+        float* pd = B.Ldet + off;
+        if (lv.s_det == 2) {
+            const int sx = (lv.w + StreamGeo<2>::UX - 1) / StreamGeo<2>::UX;
+            k_detector_stream<2><<<dim3(sx * n_seg, 1, L.batch), 32, 0, L.stream>>>(ls, img_px, px, py, pd, mk, (size_t)P.dev.mask_words, p, sx, n_seg, RL);
+        } else if (lv.s_det == 3) {
+            const int sx = (lv.w + StreamGeo<3>::UX - 1) / StreamGeo<3>::UX;
+            k_detector_stream<3><<<dim3(sx * n_seg, 1, L.batch), 32, 0, L.stream>>>(ls, img_px, px, py, pd, mk, (size_t)P.dev.mask_words, p, sx, n_seg, RL);
+        } else {
+            const int sx = (lv.w + StreamGeo<4>::UX - 1) / StreamGeo<4>::UX;
+            k_detector_stream<4><<<dim3(sx * n_seg, 1, L.batch), 32, 0, L.stream>>>(ls, img_px, px, py, pd, mk, (size_t)P.dev.mask_words, p, sx, n_seg, RL);
+        }
+        return 1;
+    }
     if (fast) {
         dim3 gf((lv.w + 63) / 64, (lv.h + 31) / 32, L.batch);
         if (lv.s_det == 2)

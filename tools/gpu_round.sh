@@ -4,7 +4,7 @@
 # gpurun copies back at most 64 MiB of gpurun_out/, so .ncu-rep files are converted to CSV on the box and
 # only small reports are kept.
 tag=${1:-x}; shift
-what=${*:-tests extract match launches full src}
+what=${*:-tests extract match launches full src srcmatch}
 mkdir -p gpurun_out
 has() { [[ " $what " == *" $1 "* ]]; }
 if has tests; then
@@ -33,8 +33,12 @@ if has full; then
   ncu -i /tmp/${tag}_full.ncu-rep --page raw --csv > gpurun_out/${tag}_full_raw.csv 2>> gpurun_out/${tag}_full.log
 fi
 if has src; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_detector_fast|k_fed|k_descriptor|k_prep_fast|k_match|k_dedup_smem|k_orientation' -c 14 -o gpurun_out/${tag}_src python tools/profile_run.py --images 4 --match 32768 > gpurun_out/${tag}_src.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${NCU_SRC_REGEX:-k_detector_stream}" -c ${NCU_SRC_COUNT:-4} -o gpurun_out/${tag}_src python tools/profile_run.py --images 8 > gpurun_out/${tag}_src.log 2>&1
   ls -la gpurun_out/${tag}_src.ncu-rep
-  if [ $(stat -c %s gpurun_out/${tag}_src.ncu-rep 2>/dev/null || echo 0) -gt 40000000 ]; then rm -f gpurun_out/${tag}_src.ncu-rep; fi
+  if [ $(stat -c %s gpurun_out/${tag}_src.ncu-rep 2>/dev/null || echo 0) -gt 30000000 ]; then rm -f gpurun_out/${tag}_src.ncu-rep; fi
+fi
+if has srcmatch; then
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_match_tc -c 1 -o gpurun_out/${tag}_srcmatch python tools/profile_run.py --no-extract --match 131072 > gpurun_out/${tag}_srcmatch.log 2>&1
+  ls -la gpurun_out/${tag}_srcmatch.ncu-rep
 fi
 du -sh gpurun_out
