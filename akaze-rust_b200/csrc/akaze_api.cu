@@ -323,7 +323,7 @@ struct akz_context {
     int device = 0;
     uint32_t max_w = 0, max_h = 0, max_batch = 0, flags = 0;
     uint32_t cand_cap = 262144, kp_cap = 65536;
-    uint32_t sub_batch = 64;           // images per pipeline sub-batch
+    uint32_t sub_batch = 128;          // images per pipeline sub-batch
     cudaStream_t stream = nullptr;     // stage A, copies, and the stream callers may time on
     cudaStream_t stream_kp = nullptr;  // stage B
     cudaStream_t stream_copy = nullptr;  // host -> device staging of the inputs, one event per sub-batch
@@ -442,6 +442,7 @@ static int ensure_lane(akz_context* c, Lane& ln, int batch) {
     CK(dalloc(A, &B.c_cls, kc));
     CK(dalloc(A, &B.c_next, kc));
     CK(dalloc(A, &B.grid, nb * 2 * (size_t)P.dev.grid_w * P.dev.grid_h));
+    CK(dalloc(A, &B.dedup_pool, nb * dedup_pool_bytes()));
     CK(dalloc(A, &B.keep_flag, kc));
     CK(dalloc(A, &B.cls_range, nb * kMaxLevels * 2));
     CK(dalloc(A, &B.plan_dev, 1));

@@ -116,6 +116,7 @@ struct Buffers {
     int* c_cls = nullptr;
     int* c_next = nullptr;
     int* grid = nullptr;                // [B][2][grid_cells]
+    unsigned char* dedup_pool = nullptr;  // [B][dedup_pool_bytes()] pools of the shared-memory cache pass
     unsigned int* n_cache = nullptr;    // [B]
     unsigned int* n_cand_total = nullptr;  // [B]
     unsigned int* keep_flag = nullptr;  // [B][kp_cap]
@@ -153,6 +154,7 @@ int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level)
 int launch_compact(const Launch& L, const Plan& P, const Buffers& B);
 // keypoints.cu
 cudaError_t init_keypoint_attributes();
+size_t dedup_pool_bytes();
 int launch_dedup(const Launch& L, const Plan& P, const Buffers& B);
 int launch_finalize(const Launch& L, const Plan& P, const Buffers& B);
 int launch_descriptors(const Launch& L, const Plan& P, const Buffers& B);

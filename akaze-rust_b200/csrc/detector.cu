@@ -401,178 +401,286 @@ __device__ __forceinline__ void h_neighbours(const float (&v)[4], float (&ext)[1
     for (int j = 0; j < S; j++) ext[8 + j] = __shfl_down_sync(0xffffffffu, v[j], 1);
 }
 
+// Row c of the pipeline. STEADY: every stage is active, no ring read clamps, no border rows to replicate,
+// all output rows inside the segment (the caller guarantees it) -> no row tests at all, and the ring slots of
+// rows c, c-S, c-2S, c-3S come in as sl[0..3] (advanced by the caller) instead of being derived from c.
+// BORDER: the strip touches the first/last S columns of the image. The steady loop is deliberately NOT
+// unrolled: an 8x unrolled body (35 KB of SASS per variant) ran 55 % slower on instruction-fetch stalls
+// (profiles/r1i: stall_no_inst 29 % of samples).
+template <int S>
+struct DetStreamCtx {
+    int W, H, lane, x0, Ya, Yb, ylo, yhi;
+    bool xin, xout, has_l, has_r;
+    int lane_l, lane_r;
+    unsigned int colmask;  // bit j: column x0+j may emit a candidate
+    float n, wn, quat, thr;
+    int ymin, ymax, wpr;
+    const float* L;
+    float *ox, *oy, *od;
+    unsigned int* m;
+};
+
+template <int S>
+struct DetStreamRegs {
+    float a[4], bo[4], lx[4], ly[4], cc[4], ee[4], dd[4], det_m[4], det_0[4], det_p[4];
+};
+
+template <int S, bool BORDER>
+__device__ __forceinline__ void det_fix_cols(const DetStreamCtx<S>& k, float (&v)[4]) {
+    if (!BORDER) return;
+    constexpr unsigned int FULL = 0xffffffffu;
+    if (k.has_l) {
+        const float t = __shfl_sync(FULL, v[S & 3], k.lane_l);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (k.x0 + j < S) v[j] = t;
+    }
+    if (k.has_r) {
+        const float t = __shfl_sync(FULL, v[(3 - S) & 3], k.lane_r & 31);
+#pragma unroll
+        for (int j = 0; j < 4; j++)
+            if (k.x0 + j > k.W - 1 - S) v[j] = t;
+    }
+}
+
+// row o of an output plane plus the border rows that replicate it (fill_border in y)
+template <int S>
+__device__ __forceinline__ void det_store_rows(const DetStreamCtx<S>& k, float* plane, int o, const float (&v)[4]) {
+    if (!k.xout) return;
+    const float4 q = make_float4(v[0], v[1], v[2], v[3]);
+    if (o >= k.Ya && o < k.Yb) st4(plane + (size_t)o * k.W + k.x0, q);
+    if (o == k.ylo)
+        for (int r = max(0, k.Ya); r < min(k.ylo, k.Yb); r++) st4(plane + (size_t)r * k.W + k.x0, q);
+    if (o == k.yhi)
+        for (int r = max(k.yhi + 1, k.Ya); r < min(k.H, k.Yb); r++) st4(plane + (size_t)r * k.W + k.x0, q);
+}
+
+template <int S, bool STEADY, bool BORDER>
+__device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStreamRegs<S>& R, float4 (*ring)[StreamGeo<S>::D][32],
+                                                int c, const float4& Lc, const int (&sl)[4]) {
+    using G = StreamGeo<S>;
+    constexpr unsigned int FULL = 0xffffffffu;
+    constexpr int M = G::D - 1;
+    const float n = k.n, wn = k.wn;
+    const int lane = k.lane;
+    // ring slots of rows c, c-S, c-2S, c-3S
+    const int s0 = STEADY ? sl[0] : (c & M);
+    const int s1 = STEADY ? sl[1] : ((c - S) & M);
+    const int o1 = c - S, o2 = c - 2 * S, o3 = o2 - 1;
+    // ---- A = H_main(Lsmooth), Bo = H_off(Lsmooth), row c (rows beyond yhi keep the registers of row yhi)
+    if (STEADY || c <= k.yhi) {
+        const float v[4] = {Lc.x, Lc.y, Lc.z, Lc.w};
+        float e[12];
+        h_neighbours<S>(v, e);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            R.a[j] = (n * e[4 + j - S] + wn * e[4 + j]) + n * e[4 + j + S];
+            R.bo[j] = e[4 + j + S] - e[4 + j - S];
+        }
+        det_fix_cols<S, BORDER>(k, R.a);
+        det_fix_cols<S, BORDER>(k, R.bo);
+    }
+    // ---- Lx = V_off(A), Ly = V_main(Bo), row o1 = c - S
+    const bool row1 = STEADY || (o1 >= k.ylo && o1 <= k.yhi);
+    if (row1) {
+        const int rm = STEADY ? sl[2] : (max(o1 - S, k.ylo) & M);
+        const float4 a_m = ring[0][rm][lane], b_m = ring[1][rm][lane], b_0 = ring[1][s1][lane];
+        R.lx[0] = R.a[0] - a_m.x; R.lx[1] = R.a[1] - a_m.y; R.lx[2] = R.a[2] - a_m.z; R.lx[3] = R.a[3] - a_m.w;
+        R.ly[0] = (n * b_m.x + wn * b_0.x) + n * R.bo[0];
+        R.ly[1] = (n * b_m.y + wn * b_0.y) + n * R.bo[1];
+        R.ly[2] = (n * b_m.z + wn * b_0.z) + n * R.bo[2];
+        R.ly[3] = (n * b_m.w + wn * b_0.w) + n * R.bo[3];
+        if (STEADY) {
+            if (k.xout) {
+                st4(k.ox + (size_t)o1 * k.W + k.x0, make_float4(R.lx[0], R.lx[1], R.lx[2], R.lx[3]));
+                st4(k.oy + (size_t)o1 * k.W + k.x0, make_float4(R.ly[0], R.ly[1], R.ly[2], R.ly[3]));
+            }
+        } else {
+            det_store_rows<S>(k, k.ox, o1, R.lx);
+            det_store_rows<S>(k, k.oy, o1, R.ly);
+        }
+    }
+    if (STEADY || c <= k.yhi) {  // after the reads above: row c may reuse the slot of row c - 2S
+        ring[0][s0][lane] = make_float4(R.a[0], R.a[1], R.a[2], R.a[3]);
+        ring[1][s0][lane] = make_float4(R.bo[0], R.bo[1], R.bo[2], R.bo[3]);
+    }
+    // ---- C = H_main(Lx), E = H_off(Lx), D = H_off(Ly), row o1
+    if (row1) {
+        float e[12];
+        h_neighbours<S>(R.lx, e);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            R.cc[j] = (n * e[4 + j - S] + wn * e[4 + j]) + n * e[4 + j + S];
+            R.ee[j] = e[4 + j + S] - e[4 + j - S];
+        }
+        h_neighbours<S>(R.ly, e);
+#pragma unroll
+        for (int j = 0; j < 4; j++) R.dd[j] = e[4 + j + S] - e[4 + j - S];
+        det_fix_cols<S, BORDER>(k, R.cc);
+        det_fix_cols<S, BORDER>(k, R.ee);
+        det_fix_cols<S, BORDER>(k, R.dd);
+    }
+    // ---- Lxx = V_off(C), Lxy = V_main(E), Lyy = V_main(D), Ldet, row o2 = c - 2S
+    if (STEADY || (o2 >= k.ylo && o2 <= k.yhi)) {
+        const int rm = STEADY ? sl[3] : (max(o2 - S, k.ylo) & M);
+        const int r0 = STEADY ? sl[2] : (o2 & M);
+        const float4 c_m = ring[2][rm][lane], e_m = ring[3][rm][lane], e_0 = ring[3][r0][lane];
+        const float4 d_m = ring[4][rm][lane], d_0 = ring[4][r0][lane];
+        const float cm[4] = {c_m.x, c_m.y, c_m.z, c_m.w}, em[4] = {e_m.x, e_m.y, e_m.z, e_m.w}, e0[4] = {e_0.x, e_0.y, e_0.z, e_0.w};
+        const float dm[4] = {d_m.x, d_m.y, d_m.z, d_m.w}, d0[4] = {d_0.x, d_0.y, d_0.z, d_0.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float lxx = R.cc[j] - cm[j];
+            const float lyy = (n * dm[j] + wn * d0[j]) + n * R.dd[j];
+            const float lxy = (n * em[j] + wn * e0[j]) + n * R.ee[j];
+            R.det_m[j] = R.det_0[j];
+            R.det_0[j] = R.det_p[j];
+            R.det_p[j] = ((lxx * lyy) - (lxy * lxy)) * k.quat;  // detector_response.rs:52
+        }
+        if (STEADY) {
+            if (k.xout) st4(k.od + (size_t)o2 * k.W + k.x0, make_float4(R.det_p[0], R.det_p[1], R.det_p[2], R.det_p[3]));
+        } else {
+            det_store_rows<S>(k, k.od, o2, R.det_p);
+        }
+    } else if (o2 > k.yhi) {  // Ldet(o2) = Ldet(yhi)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            R.det_m[j] = R.det_0[j];
+            R.det_0[j] = R.det_p[j];
+        }
+    }
+    if (row1) {
+        ring[2][s1][lane] = make_float4(R.cc[0], R.cc[1], R.cc[2], R.cc[3]);
+        ring[3][s1][lane] = make_float4(R.ee[0], R.ee[1], R.ee[2], R.ee[3]);
+        ring[4][s1][lane] = make_float4(R.dd[0], R.dd[1], R.dd[2], R.dd[3]);
+    }
+    // ---- candidates of row o3 = o2 - 1: threshold + strict 4-neighbour maximum + is_out
+    if (STEADY || (o3 >= k.Ya && o3 < k.Yb && o3 >= k.ymin && o3 <= k.ymax)) {
+        const float left = __shfl_up_sync(FULL, R.det_0[3], 1), right = __shfl_down_sync(FULL, R.det_0[0], 1);
+        unsigned int nib = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const float v = R.det_0[j];
+            const float l = j > 0 ? R.det_0[j > 0 ? j - 1 : 0] : left;
+            const float r = j < 3 ? R.det_0[j < 3 ? j + 1 : 3] : right;
+            const bool cand = v > k.thr && v > r && v > l && v > R.det_m[j] && v > R.det_p[j];
+            nib |= (cand ? 1u : 0u) << j;
+        }
+        nib &= k.colmask;
+        if (nib) atomicOr(&k.m[(size_t)o3 * k.wpr + (k.x0 >> 5)], nib << (k.x0 & 31));
+    }
+}
+
+// Lsmooth rows reach the pipeline through a 4-deep cp.async queue in shared memory (each lane copies and later
+// reads only its own 16 bytes: no barrier). Row c+3 is requested while row c is consumed. A register queue does
+// not work here: rotating it with moves touches the load's destination in the same step (27 % of all stall
+// samples in profiles/r1j), and renaming it by unrolling the loop 4x makes the body miss the instruction cache
+// (profiles/r1i, r1k: 40-55 % slower).
+__device__ __forceinline__ void cp_async16(float4* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned int)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait3() { asm volatile("cp.async.wait_group 3;" ::: "memory"); }
+
+template <int S, bool BORDER>
+__device__ __forceinline__ void det_stream_run(const DetStreamCtx<S>& k, float4 (*ring)[StreamGeo<S>::D][32], float4 (*lq)[32], int c_begin,
+                                               int c_end) {
+    using G = StreamGeo<S>;
+    DetStreamRegs<S> R;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        R.a[j] = R.bo[j] = R.lx[j] = R.ly[j] = R.cc[j] = R.ee[j] = R.dd[j] = R.det_m[j] = R.det_0[j] = R.det_p[j] = 0.0f;
+    const int lane = k.lane;
+#pragma unroll
+    for (int i = 0; i < 4; i++) lq[i][lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);  // lanes outside the image never copy
+    auto request_row = [&](int c) {  // one commit group per row, empty when there is nothing to copy
+        if (k.xin && c <= k.yhi) cp_async16(&lq[c & 3][lane], k.L + (size_t)c * k.W + k.x0);
+        cp_async_commit();
+    };
+    request_row(c_begin);
+    request_row(c_begin + 1);
+    request_row(c_begin + 2);
+    // rows [c_lo, c_hi] are steady (see det_stream_step); the others run the fully guarded step
+    const int c_lo = max(max(4 * S, k.Ya + 2 * S + 1), k.ymin + 2 * S + 1);
+    const int c_hi = min(min(k.yhi - 3, k.Yb - 1 + S), k.ymax + 2 * S + 1);
+    int c = c_begin;
+    const int no_slots[4] = {0, 0, 0, 0};
+    auto generic_until = [&](int stop) {  // rows c .. stop-1
+        for (; c < stop; c++) {
+            request_row(c + 3);
+            cp_async_wait3();
+            const float4 Lc = lq[c & 3][lane];
+            det_stream_step<S, false, BORDER>(k, R, ring, c, Lc, no_slots);
+        }
+    };
+    if (c_lo <= c_hi) {
+        generic_until(max(c_lo, c_begin));
+        constexpr int M = G::D - 1;
+        int sl[4] = {c & M, (c - S) & M, (c - 2 * S) & M, (c - 3 * S) & M};
+        const float* pl = k.L + (size_t)(c + 3) * k.W + k.x0;  // row c + 3 <= yhi
+#pragma unroll 1
+        for (; c <= c_hi; c++) {
+            if (k.xin) cp_async16(&lq[(c + 3) & 3][lane], pl);
+            cp_async_commit();
+            pl += k.W;
+            cp_async_wait3();
+            const float4 Lc = lq[c & 3][lane];
+            det_stream_step<S, true, BORDER>(k, R, ring, c, Lc, sl);
+#pragma unroll
+            for (int i = 0; i < 4; i++) sl[i] = (sl[i] + 1) & M;
+        }
+    }
+    generic_until(c_end + 1);
+}
+
 template <int S>
 __global__ void __launch_bounds__(32)
 k_detector_stream(const float* __restrict__ lsmooth, size_t img_px, float* __restrict__ oLx, float* __restrict__ oLy,
                   float* __restrict__ oLdet, unsigned int* __restrict__ mask, size_t mask_img_words, DetParams p, int strips_x,
                   int n_seg, int RL) {
     using G = StreamGeo<S>;
-    constexpr unsigned int FULL = 0xffffffffu;
-    constexpr int M = G::D - 1;
     __shared__ float4 ring[5][G::D][32];  // A, Bo, C, E, D
-    const int lane = threadIdx.x;
+    __shared__ float4 lq[4][32];          // cp.async queue of Lsmooth rows
+    DetStreamCtx<S> k;
+    k.lane = threadIdx.x;
     const int si = blockIdx.x % strips_x, sj = blockIdx.x / strips_x;
     const int img = blockIdx.z;
-    const int W = p.W, H = p.H;
-    const float n = p.n, wn = p.wn;
+    k.W = p.W;
+    k.H = p.H;
+    k.n = p.n;
+    k.wn = p.wn;
+    k.quat = p.quat;
+    k.thr = p.thr;
+    k.ymin = p.ymin;
+    k.ymax = p.ymax;
+    k.wpr = p.wpr;
     const int xb = si * G::UX - G::HX;  // first column of the strip (multiple of 4, may be negative)
-    const int x0 = xb + 4 * lane;
-    const int Ya = sj * RL, Yb = (sj == n_seg - 1) ? H : Ya + RL;
-    const bool xin = x0 >= 0 && x0 < W;
-    const bool xout = xin && x0 >= si * G::UX && x0 < (si + 1) * G::UX;
-    const int ylo = S, yhi = H - 1 - S;  // rows every pass computes; the others replicate them
-    const int c_begin = max(ylo, Ya - 1 - 2 * S), c_end = Yb + 2 * S;
-    const bool has_l = xb < S, has_r = xb + DS_W - 1 > W - 1 - S;
-    const int lane_l = (S - xb) >> 2;          // lane holding column S (component S & 3)
-    const int lane_r = (W - 1 - S - xb) >> 2;  // lane holding column W-1-S (component (3 - S) & 3: W % 4 == 0)
-    bool fl[4], fr[4];
+    k.x0 = xb + 4 * k.lane;
+    k.Ya = sj * RL;
+    k.Yb = (sj == n_seg - 1) ? p.H : k.Ya + RL;
+    k.xin = k.x0 >= 0 && k.x0 < p.W;
+    k.xout = k.xin && k.x0 >= si * G::UX && k.x0 < (si + 1) * G::UX;
+    k.ylo = S;
+    k.yhi = p.H - 1 - S;  // rows every pass computes; the others replicate them
+    k.has_l = xb < S;
+    k.has_r = xb + DS_W - 1 > p.W - 1 - S;
+    k.lane_l = (S - xb) >> 2;            // lane holding column S (component S & 3)
+    k.lane_r = (p.W - 1 - S - xb) >> 2;  // lane holding column W-1-S (component (3 - S) & 3: W % 4 == 0)
+    k.colmask = 0;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        fl[j] = x0 + j < S;
-        fr[j] = x0 + j > W - 1 - S;
-    }
+    for (int j = 0; j < 4; j++)
+        if (k.xout && k.x0 + j >= p.xmin && k.x0 + j <= p.xmax) k.colmask |= 1u << j;
     const size_t ibase = (size_t)img * img_px;
-    const float* L = lsmooth + ibase;
-    float* ox = oLx + ibase;
-    float* oy = oLy + ibase;
-    float* od = oLdet + ibase;
-    unsigned int* m = mask + (size_t)img * mask_img_words;
-
-    auto load_row = [&](int c) {
-        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (xin && c <= yhi) v = ld4(L + (size_t)c * W + x0);
-        return v;
-    };
-    auto fix_cols = [&](float(&v)[4]) {  // fill_border in x of an H-pass output
-        if (has_l) {
-            const float t = __shfl_sync(FULL, v[S & 3], lane_l);
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (fl[j]) v[j] = t;
-        }
-        if (has_r) {
-            const float t = __shfl_sync(FULL, v[(3 - S) & 3], lane_r & 31);
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (fr[j]) v[j] = t;
-        }
-    };
-    // row o of an output plane plus the border rows that replicate it (fill_border in y)
-    auto store_rows = [&](float* plane, int o, const float(&v)[4]) {
-        if (!xout) return;
-        const float4 q = make_float4(v[0], v[1], v[2], v[3]);
-        if (o >= Ya && o < Yb) st4(plane + (size_t)o * W + x0, q);
-        if (o == ylo)
-            for (int r = max(0, Ya); r < min(ylo, Yb); r++) st4(plane + (size_t)r * W + x0, q);
-        if (o == yhi)
-            for (int r = max(yhi + 1, Ya); r < min(H, Yb); r++) st4(plane + (size_t)r * W + x0, q);
-    };
-    auto clamp_lo = [&](int r) { return r < ylo ? ylo : r; };
-
-    float a[4], bo[4], lx[4], ly[4], cc[4], ee[4], dd[4], det_m[4], det_0[4], det_p[4];
-#pragma unroll
-    for (int j = 0; j < 4; j++) a[j] = bo[j] = lx[j] = ly[j] = cc[j] = ee[j] = dd[j] = det_m[j] = det_0[j] = det_p[j] = 0.0f;
-    float4 Lc = load_row(c_begin), Ln1 = load_row(c_begin + 1), Ln2 = load_row(c_begin + 2);
-
-    for (int c = c_begin; c <= c_end; c++) {
-        const float4 Ln3 = load_row(c + 3);
-        // ---- A = H_main(Lsmooth), Bo = H_off(Lsmooth), row c (rows beyond yhi keep the registers of row yhi)
-        if (c <= yhi) {
-            const float v[4] = {Lc.x, Lc.y, Lc.z, Lc.w};
-            float e[12];
-            h_neighbours<S>(v, e);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                a[j] = (n * e[4 + j - S] + wn * e[4 + j]) + n * e[4 + j + S];
-                bo[j] = e[4 + j + S] - e[4 + j - S];
-            }
-            fix_cols(a);
-            fix_cols(bo);
-        }
-        // ---- Lx = V_off(A), Ly = V_main(Bo), row o1 = c - S
-        const int o1 = c - S;
-        const bool row1 = o1 >= ylo && o1 <= yhi;
-        if (row1) {
-            const int rm = clamp_lo(o1 - S) & M;
-            const float4 a_m = ring[0][rm][lane], b_m = ring[1][rm][lane], b_0 = ring[1][o1 & M][lane];
-            lx[0] = a[0] - a_m.x; lx[1] = a[1] - a_m.y; lx[2] = a[2] - a_m.z; lx[3] = a[3] - a_m.w;
-            ly[0] = (n * b_m.x + wn * b_0.x) + n * bo[0];
-            ly[1] = (n * b_m.y + wn * b_0.y) + n * bo[1];
-            ly[2] = (n * b_m.z + wn * b_0.z) + n * bo[2];
-            ly[3] = (n * b_m.w + wn * b_0.w) + n * bo[3];
-            store_rows(ox, o1, lx);
-            store_rows(oy, o1, ly);
-        }
-        if (c <= yhi) {  // after the reads above: row c may reuse the slot of row c - 2S
-            ring[0][c & M][lane] = make_float4(a[0], a[1], a[2], a[3]);
-            ring[1][c & M][lane] = make_float4(bo[0], bo[1], bo[2], bo[3]);
-        }
-        // ---- C = H_main(Lx), E = H_off(Lx), D = H_off(Ly), row o1
-        if (row1) {
-            float e[12];
-            h_neighbours<S>(lx, e);
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                cc[j] = (n * e[4 + j - S] + wn * e[4 + j]) + n * e[4 + j + S];
-                ee[j] = e[4 + j + S] - e[4 + j - S];
-            }
-            h_neighbours<S>(ly, e);
-#pragma unroll
-            for (int j = 0; j < 4; j++) dd[j] = e[4 + j + S] - e[4 + j - S];
-            fix_cols(cc);
-            fix_cols(ee);
-            fix_cols(dd);
-        }
-        // ---- Lxx = V_off(C), Lxy = V_main(E), Lyy = V_main(D), Ldet, row o2 = c - 2S
-        const int o2 = o1 - S;
-        if (o2 >= ylo && o2 <= yhi) {
-            const int rm = clamp_lo(o2 - S) & M;
-            const float4 c_m = ring[2][rm][lane], e_m = ring[3][rm][lane], e_0 = ring[3][o2 & M][lane];
-            const float4 d_m = ring[4][rm][lane], d_0 = ring[4][o2 & M][lane];
-            const float cm[4] = {c_m.x, c_m.y, c_m.z, c_m.w}, em[4] = {e_m.x, e_m.y, e_m.z, e_m.w}, e0[4] = {e_0.x, e_0.y, e_0.z, e_0.w};
-            const float dm[4] = {d_m.x, d_m.y, d_m.z, d_m.w}, d0[4] = {d_0.x, d_0.y, d_0.z, d_0.w};
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const float lxx = cc[j] - cm[j];
-                const float lyy = (n * dm[j] + wn * d0[j]) + n * dd[j];
-                const float lxy = (n * em[j] + wn * e0[j]) + n * ee[j];
-                det_m[j] = det_0[j];
-                det_0[j] = det_p[j];
-                det_p[j] = ((lxx * lyy) - (lxy * lxy)) * p.quat;  // detector_response.rs:52
-            }
-            store_rows(od, o2, det_p);
-        } else if (o2 > yhi) {  // Ldet(o2) = Ldet(yhi)
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                det_m[j] = det_0[j];
-                det_0[j] = det_p[j];
-            }
-        }
-        if (row1) {
-            ring[2][o1 & M][lane] = make_float4(cc[0], cc[1], cc[2], cc[3]);
-            ring[3][o1 & M][lane] = make_float4(ee[0], ee[1], ee[2], ee[3]);
-            ring[4][o1 & M][lane] = make_float4(dd[0], dd[1], dd[2], dd[3]);
-        }
-        // ---- candidates of row o3 = o2 - 1: threshold + strict 4-neighbour maximum + is_out
-        const int o3 = o2 - 1;
-        if (o3 >= Ya && o3 < Yb && o3 >= p.ymin && o3 <= p.ymax) {
-            const float left = __shfl_up_sync(FULL, det_0[3], 1), right = __shfl_down_sync(FULL, det_0[0], 1);
-            unsigned int nib = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int x = x0 + j;
-                const float v = det_0[j];
-                const float l = j > 0 ? det_0[j > 0 ? j - 1 : 0] : left;
-                const float r = j < 3 ? det_0[j < 3 ? j + 1 : 3] : right;
-                const bool cand = xout && x >= p.xmin && x <= p.xmax && v > p.thr && v > r && v > l && v > det_m[j] && v > det_p[j];
-                nib |= (cand ? 1u : 0u) << j;
-            }
-            if (nib) atomicOr(&m[(size_t)o3 * p.wpr + (x0 >> 5)], nib << (x0 & 31));
-        }
-        Lc = Ln1;
-        Ln1 = Ln2;
-        Ln2 = Ln3;
-    }
+    k.L = lsmooth + ibase;
+    k.ox = oLx + ibase;
+    k.oy = oLy + ibase;
+    k.od = oLdet + ibase;
+    k.m = mask + (size_t)img * mask_img_words;
+    const int c_begin = max(k.ylo, k.Ya - 1 - 2 * S), c_end = k.Yb + 2 * S;
+    if (k.has_l || k.has_r)
+        det_stream_run<S, true>(k, ring, lq, c_begin, c_end);
+    else
+        det_stream_run<S, false>(k, ring, lq, c_begin, c_end);
 }
 
 // ---- bitmask -> ordered list ------------------------------------------------------------------

@@ -174,23 +174,30 @@ __device__ __forceinline__ bool image_fits_smem_pass(const PlanDev* plan, const 
     return true;
 }
 
+// Only the hash-grid heads live in shared memory (34 KB). The two pools are per-image scratch in global
+// memory: an entry is touched once or twice per candidate and stays in L1/L2, while a 181 KB shared-memory
+// working set kept every other kernel of the pipeline (which runs concurrently on the second stream) off the
+// SMs that hosted a cache-pass block. Lanes of the one warp exchange pool entries through global memory
+// ordered by __syncwarp().
 struct DedupSmem {
+    unsigned short heads[2][kMaxGridCells];
+};
+struct DedupPool {
     float px[2][kPool];
     float py[2][kPool];
     float presp[2][kPool];
     unsigned int pslot[2][kPool];  // global cache slot; 0xffffffff = dead (replaced)
     unsigned short pnext[2][kPool];
-    unsigned short heads[2][kMaxGridCells];
 };
 
 __global__ void __launch_bounds__(32)
 k_dedup_smem(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ cand, const unsigned int* __restrict__ level_off,
              const float* __restrict__ ldet_plane, int batch, unsigned int cand_cap, unsigned int kp_cap, float* __restrict__ c_x,
              float* __restrict__ c_y, float* __restrict__ c_resp, int* __restrict__ c_cls, unsigned int* __restrict__ n_cache,
-             unsigned int* __restrict__ err_flags) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    DedupSmem& S = *reinterpret_cast<DedupSmem*>(smem_raw);
+             unsigned int* __restrict__ err_flags, DedupPool* pools) {
+    __shared__ DedupSmem S;
     const int img = blockIdx.x;
+    DedupPool& G = pools[img];
     const int lane = threadIdx.x;
     const unsigned int FULL = 0xffffffffu;
     const unsigned int* cl = cand + (size_t)img * cand_cap;
@@ -212,11 +219,11 @@ k_dedup_smem(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ 
 
     auto flush = [&](int which, int cls) {
         for (int i = lane; i < cnt[which]; i += 32) {
-            const unsigned int s = S.pslot[which][i];
+            const unsigned int s = G.pslot[which][i];
             if (s != 0xffffffffu) {
-                c_x[s] = S.px[which][i];
-                c_y[s] = S.py[which][i];
-                c_resp[s] = S.presp[which][i];
+                c_x[s] = G.px[which][i];
+                c_y[s] = G.py[which][i];
+                c_resp[s] = G.presp[which][i];
                 c_cls[s] = cls;
             }
         }
@@ -279,14 +286,14 @@ k_dedup_smem(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ 
                         const int cell = (cy0 + cc / nx) * gw + (cx0 + cc % nx);
                         unsigned short e = S.heads[which][cell];
                         while (e != kNil) {
-                            const float dx = qx - S.px[which][e], dy = qy - S.py[which][e];
+                            const float dx = qx - G.px[which][e], dy = qy - G.py[which][e];
                             const float dist = dx * dx + dy * dy;
-                            const unsigned int s = S.pslot[which][e];  // 0xffffffff = replaced (dead) entry: never < best
+                            const unsigned int s = G.pslot[which][e];  // 0xffffffff = replaced (dead) entry: never < best
                             if (dist <= size_sq && s < best) {
                                 best = s;
                                 best_ref = ((unsigned int)which << 16) | e;
                             }
-                            e = S.pnext[which][e];
+                            e = G.pnext[which][e];
                         }
                     }
                 }
@@ -305,7 +312,7 @@ k_dedup_smem(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ 
                 int act = 0;
                 if (active) {
                     if (best == 0xffffffffu) act = 1;
-                    else if (resp > S.presp[bw][be]) act = 2;  // scale_space_extrema.rs:67
+                    else if (resp > G.presp[bw][be]) act = 2;  // scale_space_extrema.rs:67
                 }
                 const float fx = (float)px * ratio + hr, fy = (float)py * ratio + hr;  // :89-92
                 // conflict rule: an earlier candidate a of this step that writes changes the decision of b only if
@@ -336,11 +343,11 @@ k_dedup_smem(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ 
                 if (commits && act != 0) {
                     const unsigned int slot = (act == 1) ? n + __popc(amask & lt) : best;
                     const int at = cnt[cur] + __popc(wmask & lt);  // <= candidates of this level <= kPool
-                    if (act == 2) S.pslot[bw][be] = 0xffffffffu;  // the old occupant is dead; it stays on its cell list
-                    S.px[cur][at] = fx;
-                    S.py[cur][at] = fy;
-                    S.presp[cur][at] = resp;
-                    S.pslot[cur][at] = slot;
+                    if (act == 2) G.pslot[bw][be] = 0xffffffffu;  // the old occupant is dead; it stays on its cell list
+                    G.px[cur][at] = fx;
+                    G.py[cur][at] = fy;
+                    G.presp[cur][at] = resp;
+                    G.pslot[cur][at] = slot;
                     const int ncx = min(gw - 1, max(0, (int)fx >> gshift));
                     const int ncy = min(gh - 1, max(0, (int)fy >> gshift));
                     const int ncl = ncy * gw + ncx;
@@ -349,7 +356,7 @@ k_dedup_smem(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ 
                     const int rank = __popc(same & lt), nsame = __popc(same);
                     for (int r = 0; r < nsame; r++) {
                         if (r == rank) {
-                            S.pnext[cur][at] = S.heads[cur][ncl];
+                            G.pnext[cur][at] = S.heads[cur][ncl];
                             S.heads[cur][ncl] = (unsigned short)at;
                         }
                         __syncwarp(same);
@@ -758,14 +765,14 @@ k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plan
 
 }  // namespace
 
-cudaError_t init_keypoint_attributes() {
-    return cudaFuncSetAttribute(k_dedup_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(DedupSmem));
-}
+cudaError_t init_keypoint_attributes() { return cudaSuccess; }
+
+size_t dedup_pool_bytes() { return sizeof(DedupPool); }
 
 int launch_dedup(const Launch& L, const Plan& P, const Buffers& B) {
     // every image is handled by exactly one of the two kernels (image_fits_smem_pass)
-    k_dedup_smem<<<L.batch, 32, sizeof(DedupSmem), L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap,
-                                                                L.kp_cap, B.c_x, B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags);
+    k_dedup_smem<<<L.batch, 32, 0, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap, L.kp_cap, B.c_x,
+                                               B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags, (DedupPool*)B.dedup_pool);
     k_dedup<<<L.batch, 32, 0, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap, L.kp_cap,
                                            B.c_x, B.c_y, B.c_resp, B.c_cls, B.c_next, B.grid, B.n_cache, B.err_flags);
     return 2;
