@@ -33,7 +33,7 @@ if has full; then
   ncu -i /tmp/${tag}_full.ncu-rep --page raw --csv > gpurun_out/${tag}_full_raw.csv 2>> gpurun_out/${tag}_full.log
 fi
 if has src; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${NCU_SRC_REGEX:-k_detector_stream}" -c ${NCU_SRC_COUNT:-4} -o gpurun_out/${tag}_src python tools/profile_run.py --images ${NCU_SRC_IMAGES:-8} > gpurun_out/${tag}_src.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"${NCU_SRC_REGEX:-k_detector_stream}" -c ${NCU_SRC_COUNT:-4} -o gpurun_out/${tag}_src python tools/profile_run.py --images ${NCU_SRC_IMAGES:-8} > gpurun_out/${tag}_src.log 2>&1
   ls -la gpurun_out/${tag}_src.ncu-rep
   if [ $(stat -c %s gpurun_out/${tag}_src.ncu-rep 2>/dev/null || echo 0) -gt 30000000 ]; then rm -f gpurun_out/${tag}_src.ncu-rep; fi
 fi
