@@ -324,6 +324,7 @@ struct akz_context {
     uint32_t max_w = 0, max_h = 0, max_batch = 0, flags = 0;
     uint32_t cand_cap = 262144, kp_cap = 65536;
     uint32_t sub_batch = 128;          // images per pipeline sub-batch
+    bool sub_batch_auto = true;        // chosen from the free device memory when the plan changes (see prepare)
     cudaStream_t stream = nullptr;     // stage A, copies, and the stream callers may time on
     cudaStream_t stream_kp = nullptr;  // stage B
     cudaStream_t stream_copy = nullptr;  // host -> device staging of the inputs, one event per sub-batch
@@ -522,6 +523,18 @@ static int prepare(akz_context* c, uint32_t n, uint32_t w, uint32_t h, const akz
         free_buffers(c);
         c->plan = np;
         c->have_plan = true;
+        if (c->sub_batch_auto) {
+            // Large sub-batches fill the GPU in the small octaves, give the latency-bound cache pass one warp per
+            // image to hide behind and shorten the pipeline tail: up to 256 images per lane, as long as the two
+            // lanes take at most half of the memory that is free right now (B200: 180 GB).
+            size_t free_b = 0, total_b = 0;
+            CK(cudaMemGetInfo(&free_b, &total_b));
+            const size_t n0 = (size_t)w * h;
+            const size_t per_image = 4 * (4 * (size_t)np.dev.plane_px + 3 * n0) + 4 * (size_t)np.dev.mask_words + 4 * (size_t)c->cand_cap +
+                                     40 * (size_t)c->kp_cap + dedup_pool_bytes() + (1 << 16);
+            const size_t fit = (free_b / 2) / (2 * per_image);
+            c->sub_batch = (uint32_t)std::max<size_t>(16, std::min<size_t>(256, fit));
+        }
     }
     const uint32_t m = sub_batch_of(c, n);
     int rc = ensure_lane(c, c->lane[0], (int)m);
@@ -803,7 +816,10 @@ int akz_create(int device, uint32_t max_width, uint32_t max_height, uint32_t max
     c->flags = flags;
     if (const char* sbe = getenv("AKZ_SUB_BATCH")) {
         const int v = atoi(sbe);
-        if (v > 0) c->sub_batch = (uint32_t)v;
+        if (v > 0) {
+            c->sub_batch = (uint32_t)v;
+            c->sub_batch_auto = false;
+        }
     }
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->stream_kp, cudaStreamNonBlocking));
@@ -895,6 +911,7 @@ int akz_context_set_sub_batch(akz_context* c, uint32_t images) {
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->stream_kp);
     c->sub_batch = images;
+    c->sub_batch_auto = false;
     return AKZ_OK;
 }
 

@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--workload", default="extract", choices=["extract", "match"])
     ap.add_argument("--images", type=int, default=1024, help="images per step and per GPU (configs[2]: 1024)")
     ap.add_argument("--unique", type=int, default=128, help="distinct synthetic images (cycled to fill a step)")
-    ap.add_argument("--batch", type=int, default=512, help="images per engine call")
+    ap.add_argument("--batch", type=int, default=1024, help="images per engine call")
     ap.add_argument("--sub-batch", type=int, default=0, help="images per pipeline sub-batch (0 = library default)")
     ap.add_argument("--match-n", type=int, default=1 << 20, help="queries = database size for --workload match")
     ap.add_argument("--match-path", default="auto", choices=["auto", "popc", "tensor"], help="matcher kernel (auto = tensor at these sizes)")

@@ -125,7 +125,7 @@ int akz_context_set_limits(akz_context *ctx, uint32_t max_candidates, uint32_t m
 
 /* A call of n images is cut into sub-batches of `images` that flow through a two-stage software pipeline
  * (stencil stages of sub-batch i+1 overlap the keypoint stages and the result download of sub-batch i).
- * Default 128; memory per in-flight image is about 0.2 GB at 1080p. Environment override: AKZ_SUB_BATCH. */
+ * Default: up to 256, chosen so that both lanes fit in half of the free device memory; memory per in-flight image is about 0.2 GB at 1080p. Environment override: AKZ_SUB_BATCH. */
 int akz_context_set_sub_batch(akz_context *ctx, uint32_t images);
 
 /* Which kernel akz_match_top2* runs: AUTO picks the tcgen05 int8 path (matcher_tc.cu) for nq*ndb >= 2^20 pairs
