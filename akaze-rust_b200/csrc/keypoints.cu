@@ -467,7 +467,7 @@ __global__ void k_filter_refine(const PlanDev* __restrict__ plan, const float* _
 // one block per image: exclusive scan of keep_flag -> output slot, survivors counted
 __global__ void __launch_bounds__(1024)
 k_keep_scan(unsigned int* __restrict__ keep_flag, const unsigned int* __restrict__ n_cache, unsigned int* __restrict__ n_kp,
-            unsigned int kp_cap, int* __restrict__ inv) {
+            unsigned int kp_cap) {
     __shared__ unsigned int warp_sums[32];
     __shared__ unsigned int carry;
     const int img = blockIdx.x;
@@ -497,10 +497,7 @@ k_keep_scan(unsigned int* __restrict__ keep_flag, const unsigned int* __restrict
         __syncthreads();
         const unsigned int excl = carry + (wid ? warp_sums[wid - 1] : 0) + incl - v;
         // encode: bit 31 = keep, low bits = output position
-        if (i < n) {
-            kf[i] = (v ? 0x80000000u : 0u) | excl;
-            if (v) inv[(size_t)img * kp_cap + excl] = (int)i;  // output position -> cache slot
-        }
+        if (i < n) kf[i] = (v ? 0x80000000u : 0u) | excl;
         __syncthreads();
         if (tid == 1023) carry = excl + v;
         __syncthreads();
@@ -592,129 +589,6 @@ k_orientation(const PlanDev* __restrict__ plan, const float* __restrict__ lx_pla
         kp.angle = angle;
         kps[o + pos] = kp;
         if (oob) atomicOr(&err_flags[img], (unsigned int)kErrBounds);
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// K5c', the orientation kernel in use: same arithmetic as k_orientation above, restructured in two phases
-// per group of 32 surviving keypoints (dense output positions, through the inverse index of k_keep_scan):
-//   A. the whole warp gathers the 109 samples of one keypoint at a time (lanes = samples: one warp-wide gather
-//      touches the few cache lines of a 12s x 12s window instead of 32 unrelated keypoints) and parks
-//      gw*Lx, gw*Ly in shared memory, transposed to [sample][keypoint];
-//   B. each lane runs the strictly sequential f32 accumulation of its own keypoint from shared memory. The
-//      first window that contains pi/4 compacts the samples with res_y > 0 in place (order kept), the other
-//      five re-add that shorter list.
-// ------------------------------------------------------------------------------------------------
-constexpr int kOrWarps = 2;
-constexpr int kOrSamples = 109;
-constexpr int kOrSmemBytes = kOrWarps * 2 * kOrSamples * 32 * (int)sizeof(float) + 3 * 128 * (int)sizeof(float);
-
-__global__ void __launch_bounds__(32 * kOrWarps)
-k_orientation_warp(const PlanDev* __restrict__ plan, const float* __restrict__ lx_plane, const float* __restrict__ ly_plane, int batch,
-                   unsigned int kp_cap, const float* __restrict__ r_x, const float* __restrict__ r_y, const float* __restrict__ c_resp,
-                   const int* __restrict__ c_cls, const int* __restrict__ inv, const unsigned int* __restrict__ n_kp,
-                   akz_keypoint* __restrict__ kps, unsigned int* __restrict__ err_flags) {
-    extern __shared__ __align__(16) float or_smem[];
-    constexpr unsigned int FULL = 0xffffffffu;
-    float* s_gw = or_smem;                 // [128] gauss weight of sample k
-    float* s_a = s_gw + 128;               // [128] x offset (in units of s)
-    float* s_b = s_a + 128;                // [128] y offset
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    float* rx = s_b + 128 + (size_t)wib * 2 * kOrSamples * 32;  // [sample][keypoint]
-    float* ry = rx + kOrSamples * 32;
-    if (threadIdx.x == 0) {  // sample order of scale_space_extrema.rs:288-300
-        int idx = 0;
-        for (int a = -6; a <= 6; a++)
-            for (int b = -6; b <= 6; b++)
-                if (a * a + b * b < 36) {
-                    s_gw[idx] = c_gauss25[a < 0 ? -a : a][b < 0 ? -b : b];
-                    s_a[idx] = (float)a;
-                    s_b[idx] = (float)b;
-                    idx++;
-                }
-    }
-    __syncthreads();
-    const int img = blockIdx.y;
-    const unsigned int n = min(n_kp[img], kp_cap);
-    const size_t o = (size_t)img * kp_cap;
-    const unsigned long long wmask = plan->orient_window_mask;
-    const int nwin = plan->n_orient_windows;
-    for (unsigned int base = (blockIdx.x * kOrWarps + wib) * 32; base < n; base += gridDim.x * kOrWarps * 32) {
-        const unsigned int pos = base + lane;
-        const bool active = pos < n;
-        const int i = active ? inv[o + pos] : 0;
-        const int cls = active ? c_cls[o + i] : 0;
-        const float ptx = active ? r_x[o + i] : 0.0f, pty = active ? r_y[o + i] : 0.0f;
-        bool oob = false;
-        // ---- phase A
-        const int cnt = min(32u, n - base);
-        for (int kk = 0; kk < cnt; kk++) {
-            const int kcls = __shfl_sync(FULL, cls, kk);
-            const LevelDev& lv = plan->lv[kcls];
-            const float ratio = lv.ratio, s = lv.s_smp;
-            const float xf = __shfl_sync(FULL, ptx, kk) / ratio, yf = __shfl_sync(FULL, pty, kk) / ratio;
-            const size_t lbase = (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
-            const float* Lx = lx_plane + lbase;
-            const float* Ly = ly_plane + lbase;
-            for (int k = lane; k < kOrSamples; k += 32) {
-                int iy = (int)roundf(yf + s_b[k] * s);
-                int ix = (int)roundf(xf + s_a[k] * s);
-                if (ix < 0 || iy < 0 || ix >= lv.w || iy >= lv.h) {
-                    oob = true;
-                    ix = min(max(ix, 0), lv.w - 1);
-                    iy = min(max(iy, 0), lv.h - 1);
-                }
-                const float gw = s_gw[k];
-                const size_t at = (size_t)iy * lv.w + ix;
-                rx[k * 32 + kk] = gw * Lx[at];
-                ry[k * 32 + kk] = gw * Ly[at];
-            }
-        }
-        __syncwarp();
-        // ---- phase B
-        if (active) {
-            float sum_x = 0.0f, sum_y = 0.0f, maxv = 0.0f, angle = 0.0f;
-            int np = -1;  // number of samples with res_y > 0 once the first pass has compacted them
-            for (int w = 0; w < nwin; w++) {
-                if (!((wmask >> w) & 1ull)) continue;  // sums unchanged: val cannot exceed max
-                if (np < 0) {
-                    np = 0;
-                    for (int k = 0; k < kOrSamples; k++) {
-                        const float vx = rx[k * 32 + lane], vy = ry[k * 32 + lane];
-                        if (vy > 0.0f) {
-                            sum_x = sum_x + vx;
-                            sum_y = sum_y + vy;
-                            rx[np * 32 + lane] = vx;
-                            ry[np * 32 + lane] = vy;
-                            np++;
-                        }
-                    }
-                } else {
-                    for (int k = 0; k < np; k++) {
-                        sum_x = sum_x + rx[k * 32 + lane];
-                        sum_y = sum_y + ry[k * 32 + lane];
-                    }
-                }
-                const float val = sum_x * sum_x + sum_y * sum_y;
-                if (val > maxv) {
-                    maxv = val;
-                    // f32::atan2 -> libm atan2f; evaluated in f64 and rounded once
-                    angle = (float)atan2((double)sum_y, (double)sum_x);
-                }
-            }
-            const LevelDev& lv = plan->lv[cls];
-            akz_keypoint kp;
-            kp.x = ptx;
-            kp.y = pty;
-            kp.response = c_resp[o + i];
-            kp.size = lv.kp_size;
-            kp.octave = (uint32_t)lv.octave;
-            kp.class_id = (uint32_t)cls;
-            kp.angle = angle;
-            kps[o + pos] = kp;
-        }
-        if (oob) atomicOr(&err_flags[img], (unsigned int)kErrBounds);
-        __syncwarp();
     }
 }
 
@@ -891,9 +765,7 @@ k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plan
 
 }  // namespace
 
-cudaError_t init_keypoint_attributes() {
-    return cudaFuncSetAttribute(k_orientation_warp, cudaFuncAttributeMaxDynamicSharedMemorySize, kOrSmemBytes);
-}
+cudaError_t init_keypoint_attributes() { return cudaSuccess; }
 
 size_t dedup_pool_bytes() { return sizeof(DedupPool); }
 
@@ -913,10 +785,10 @@ int launch_finalize(const Launch& L, const Plan& P, const Buffers& B) {
     k_class_ranges<<<L.batch, 256, 0, L.stream>>>(B.c_cls, B.n_cache, L.kp_cap, B.cls_range);
     k_filter_refine<<<g1, 256, 0, L.stream>>>(B.plan_dev, B.Ldet, L.batch, L.kp_cap, B.c_x, B.c_y, B.c_cls, B.n_cache, B.cls_range,
                                               r_x, r_y, B.keep_flag);
-    k_keep_scan<<<L.batch, 1024, 0, L.stream>>>(B.keep_flag, B.n_cache, B.n_kp, L.kp_cap, B.c_next);  // c_next is free after the cache pass
-    dim3 g3(24, L.batch);
-    k_orientation_warp<<<g3, 32 * kOrWarps, kOrSmemBytes, L.stream>>>(B.plan_dev, B.Lx, B.Ly, L.batch, L.kp_cap, r_x, r_y, B.c_resp, B.c_cls,
-                                                                     B.c_next, B.n_kp, B.kps, B.err_flags);
+    k_keep_scan<<<L.batch, 1024, 0, L.stream>>>(B.keep_flag, B.n_cache, B.n_kp, L.kp_cap);
+    dim3 g3(16, L.batch);
+    k_orientation<<<g3, 128, 0, L.stream>>>(B.plan_dev, B.Lx, B.Ly, L.batch, L.kp_cap, r_x, r_y, B.c_resp, B.c_cls, B.keep_flag,
+                                            B.n_cache, B.kps, B.err_flags);
     return 4;
 }
 
