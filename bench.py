@@ -360,7 +360,7 @@ def run_extract(args):
     chunks_px = 0.0  # FED: pixels x launches (each launch reads Lt+Lflow, writes Lt = 12 B/px)
     for o, ns in enumerate(([3, 3, 4], [4, 5, 6, 7], [8, 10, 12, 14], [17, 20, 24, 29])):
         for nsteps in ns:
-            chunks_px += (px / 4 ** o) * ((nsteps + 4) // 5)
+            chunks_px += (px / 4 ** o) * ((nsteps + 7) // 8)  # k_fed runs up to 8 steps per launch
     alg = {  # algorithmic HBM bytes per image of each stage as implemented
         "fed": 12.0 * chunks_px,
         "detector": 16.0 * sum_px,
@@ -382,11 +382,24 @@ def run_extract(args):
     else:
         ach = 0.0
     per_launch = st[dom][0] / max(1, st[dom][1])
+    # measured DRAM traffic of the stage from the committed ncu capture, scaled to this run's average launch
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "r1w_stage_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as fh:
+            tj = json.load(fh)
+        if dom in tj["stages"]:
+            traffic = tj["stages"][dom]["dram_bytes_per_image"] * n_img / max(1, st[dom][1])
+            traffic_src = "profiles/r1w_stage_traffic.json (ncu --set full, dram__bytes_read+write, 4-image capture: part of the planes stays in L2)"
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src, "avg_launch_ms": per_launch,
+                "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "avg_launch_ms": per_launch,
+                "algorithmic_bytes_per_launch": (alg[dom] * n_img / max(1, st[dom][1])) if dom in alg else None,
                 "algorithmic_bytes_per_image": alg.get(dom),
                 "note": "stage timed alone by CUDA events inside the library (serialised timing pass); the stencil kernels are "
-                        "instruction-issue bound, not DRAM bound (profiles/), so frac is far below 1 by construction"}
+                        "instruction-issue bound, not DRAM bound (profiles/r1w_ncu_summary.csv), so frac is far below 1 by construction; "
+                        "fp32_ridge_frac is the fraction of the FP32 non-FMA peak (SURVEY 8d: 724 flop per input pixel, 37.2 TFLOP/s) the "
+                        "stencil stages reach",
+                "fp32_ridge_frac": (724.0 * px / 37.2e12) / (1e-3 * sum(st[k][0] for k in ("level0", "contrast", "prep", "fed", "detector") if k in st) / n_img)}
     pipe_ach = ALG_BYTES_PER_PX * px * (n_img * args.steps) / (ms / 1000.0) / 1e9
     roofline_pipeline = {"bound": "hbm", "achieved": pipe_ach, "peak": peak, "unit": "GB/s", "frac": pipe_ach / peak,
                          "algorithmic_bytes_per_image": ALG_BYTES_PER_PX * px}
