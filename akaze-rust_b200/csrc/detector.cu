@@ -17,6 +17,8 @@
 #include <algorithm>
 #include <cstdlib>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tile_util.cuh"
 
@@ -385,7 +387,7 @@ template <int S>
 struct StreamGeo {
     static constexpr int HX = ((2 * S + 1) + 3) & ~3;  // x halo: Ldet is needed one column beyond the strip's outputs
     static constexpr int UX = DS_W - 2 * HX;           // output columns per strip
-    static constexpr int D = (S == 2) ? 4 : 8;         // ring depth: power of two >= 2S
+    static constexpr int D = 2 * S;                    // ring depth: exactly the rows a V pass looks back (row c reuses the slot of row c - 2S)
 };
 
 // ext[0..3] = left lane's v, ext[4..7] = v, ext[8..11] = right lane's v (only what a +-S tap touches is fetched)
@@ -455,17 +457,24 @@ __device__ __forceinline__ void det_store_rows(const DetStreamCtx<S>& k, float* 
         for (int r = max(k.yhi + 1, k.Ya); r < min(k.H, k.Yb); r++) st4(plane + (size_t)r * k.W + k.x0, q);
 }
 
+// where the steady rows store: Lx/Ly row c-S, Ldet row c-2S, mask word of row c-2S-1 (advanced one row per step by the
+// caller, so the steady body does no 64-bit index arithmetic)
+struct DetSteadyPtrs {
+    float *px, *py, *pd;
+    unsigned int* pm;
+};
+
 template <int S, bool STEADY, bool BORDER>
 __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStreamRegs<S>& R, float4 (*ring)[StreamGeo<S>::D][32],
-                                                int c, const float4& Lc, const int (&sl)[4]) {
+                                                int c, const float4& Lc, const int (&sl)[2], const DetSteadyPtrs& sp) {
     using G = StreamGeo<S>;
     constexpr unsigned int FULL = 0xffffffffu;
-    constexpr int M = G::D - 1;
+    constexpr int D = G::D;
     const float n = k.n, wn = k.wn;
     const int lane = k.lane;
     // ring slots of rows c, c-S, c-2S, c-3S
-    const int s0 = STEADY ? sl[0] : (c & M);
-    const int s1 = STEADY ? sl[1] : ((c - S) & M);
+    const int s0 = STEADY ? sl[0] : (c % D);
+    const int s1 = STEADY ? sl[1] : ((c - S) % D);
     const int o1 = c - S, o2 = c - 2 * S, o3 = o2 - 1;
     // ---- A = H_main(Lsmooth), Bo = H_off(Lsmooth), row c (rows beyond yhi keep the registers of row yhi)
     if (STEADY || c <= k.yhi) {
@@ -483,7 +492,7 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
     // ---- Lx = V_off(A), Ly = V_main(Bo), row o1 = c - S
     const bool row1 = STEADY || (o1 >= k.ylo && o1 <= k.yhi);
     if (row1) {
-        const int rm = STEADY ? sl[2] : (max(o1 - S, k.ylo) & M);
+        const int rm = STEADY ? sl[0] : (max(o1 - S, k.ylo) % D);  // row c - 2S shares the slot of row c
         const float4 a_m = ring[0][rm][lane], b_m = ring[1][rm][lane], b_0 = ring[1][s1][lane];
         R.lx[0] = R.a[0] - a_m.x; R.lx[1] = R.a[1] - a_m.y; R.lx[2] = R.a[2] - a_m.z; R.lx[3] = R.a[3] - a_m.w;
         R.ly[0] = (n * b_m.x + wn * b_0.x) + n * R.bo[0];
@@ -492,8 +501,8 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
         R.ly[3] = (n * b_m.w + wn * b_0.w) + n * R.bo[3];
         if (STEADY) {
             if (k.xout) {
-                st4(k.ox + (size_t)o1 * k.W + k.x0, make_float4(R.lx[0], R.lx[1], R.lx[2], R.lx[3]));
-                st4(k.oy + (size_t)o1 * k.W + k.x0, make_float4(R.ly[0], R.ly[1], R.ly[2], R.ly[3]));
+                st4(sp.px, make_float4(R.lx[0], R.lx[1], R.lx[2], R.lx[3]));
+                st4(sp.py, make_float4(R.ly[0], R.ly[1], R.ly[2], R.ly[3]));
             }
         } else {
             det_store_rows<S>(k, k.ox, o1, R.lx);
@@ -522,8 +531,8 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
     }
     // ---- Lxx = V_off(C), Lxy = V_main(E), Lyy = V_main(D), Ldet, row o2 = c - 2S
     if (STEADY || (o2 >= k.ylo && o2 <= k.yhi)) {
-        const int rm = STEADY ? sl[3] : (max(o2 - S, k.ylo) & M);
-        const int r0 = STEADY ? sl[2] : (o2 & M);
+        const int rm = STEADY ? sl[1] : (max(o2 - S, k.ylo) % D);  // row c - 3S shares the slot of row c - S
+        const int r0 = STEADY ? sl[0] : ((o2 + 2 * D) % D);
         const float4 c_m = ring[2][rm][lane], e_m = ring[3][rm][lane], e_0 = ring[3][r0][lane];
         const float4 d_m = ring[4][rm][lane], d_0 = ring[4][r0][lane];
         const float cm[4] = {c_m.x, c_m.y, c_m.z, c_m.w}, em[4] = {e_m.x, e_m.y, e_m.z, e_m.w}, e0[4] = {e_0.x, e_0.y, e_0.z, e_0.w};
@@ -538,7 +547,7 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
             R.det_p[j] = ((lxx * lyy) - (lxy * lxy)) * k.quat;  // detector_response.rs:52
         }
         if (STEADY) {
-            if (k.xout) st4(k.od + (size_t)o2 * k.W + k.x0, make_float4(R.det_p[0], R.det_p[1], R.det_p[2], R.det_p[3]));
+            if (k.xout) st4(sp.pd, make_float4(R.det_p[0], R.det_p[1], R.det_p[2], R.det_p[3]));
         } else {
             det_store_rows<S>(k, k.od, o2, R.det_p);
         }
@@ -563,11 +572,16 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
             const float v = R.det_0[j];
             const float l = j > 0 ? R.det_0[j > 0 ? j - 1 : 0] : left;
             const float r = j < 3 ? R.det_0[j < 3 ? j + 1 : 3] : right;
-            const bool cand = v > k.thr && v > r && v > l && v > R.det_m[j] && v > R.det_p[j];
-            nib |= (cand ? 1u : 0u) << j;
+            // v > thr && v > r && v > l && v > up && v > down  ==  v > max(thr, r, l, up, down): Ldet of a u8 image is
+            // finite, so no NaN can make the two forms differ (two 3-input FMNMX and one compare instead of five)
+            const float hi = fmaxf(fmaxf(fmaxf(k.thr, r), l), fmaxf(R.det_m[j], R.det_p[j]));
+            nib |= (v > hi ? 1u : 0u) << j;
         }
         nib &= k.colmask;
-        if (nib) atomicOr(&k.m[(size_t)o3 * k.wpr + (k.x0 >> 5)], nib << (k.x0 & 31));
+        if (nib) {
+            if (STEADY) atomicOr(sp.pm, nib << (k.x0 & 31));
+            else atomicOr(&k.m[(size_t)o3 * k.wpr + (k.x0 >> 5)], nib << (k.x0 & 31));
+        }
     }
 }
 
@@ -604,20 +618,29 @@ __device__ __forceinline__ void det_stream_run(const DetStreamCtx<S>& k, float4 
     const int c_lo = max(max(4 * S, k.Ya + 2 * S + 1), k.ymin + 2 * S + 1);
     const int c_hi = min(min(k.yhi - 3, k.Yb - 1 + S), k.ymax + 2 * S + 1);
     int c = c_begin;
-    const int no_slots[4] = {0, 0, 0, 0};
+    const int no_slots[2] = {0, 0};
+    const DetSteadyPtrs no_ptrs = {nullptr, nullptr, nullptr, nullptr};
     auto generic_until = [&](int stop) {  // rows c .. stop-1
         for (; c < stop; c++) {
             request_row(c + 3);
             cp_async_wait3();
             const float4 Lc = lq[c & 3][lane];
-            det_stream_step<S, false, BORDER>(k, R, ring, c, Lc, no_slots);
+            det_stream_step<S, false, BORDER>(k, R, ring, c, Lc, no_slots, no_ptrs);
         }
     };
     if (c_lo <= c_hi) {
         generic_until(max(c_lo, c_begin));
-        constexpr int M = G::D - 1;
-        int sl[4] = {c & M, (c - S) & M, (c - 2 * S) & M, (c - 3 * S) & M};
+        int sl[2] = {c % G::D, (c - S) % G::D};  // c >= 4S here
         const float* pl = k.L + (size_t)(c + 3) * k.W + k.x0;  // row c + 3 <= yhi
+        DetSteadyPtrs sp;
+        sp.px = k.ox + (ptrdiff_t)(c - S) * k.W + k.x0;
+        sp.py = k.oy + (ptrdiff_t)(c - S) * k.W + k.x0;
+        sp.pd = k.od + (ptrdiff_t)(c - 2 * S) * k.W + k.x0;
+        sp.pm = k.m + (ptrdiff_t)(c - 2 * S - 1) * k.wpr + (k.x0 >> 5);
+        auto advance = [&]() {
+#pragma unroll
+            for (int i = 0; i < 2; i++) sl[i] = (sl[i] + 1 == G::D) ? 0 : sl[i] + 1;
+        };
 #pragma unroll 1
         for (; c <= c_hi; c++) {
             if (k.xin) cp_async16(&lq[(c + 3) & 3][lane], pl);
@@ -625,9 +648,12 @@ __device__ __forceinline__ void det_stream_run(const DetStreamCtx<S>& k, float4 
             pl += k.W;
             cp_async_wait3();
             const float4 Lc = lq[c & 3][lane];
-            det_stream_step<S, true, BORDER>(k, R, ring, c, Lc, sl);
-#pragma unroll
-            for (int i = 0; i < 4; i++) sl[i] = (sl[i] + 1) & M;
+            det_stream_step<S, true, BORDER>(k, R, ring, c, Lc, sl, sp);
+            advance();
+            sp.px += k.W;
+            sp.py += k.W;
+            sp.pd += k.W;
+            sp.pm += k.wpr;
         }
     }
     generic_until(c_end + 1);
@@ -845,16 +871,14 @@ int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level)
         float* px = B.Lx + off;
         float* py = B.Ly + off;
         float* pd = B.Ldet + off;
-        if (lv.s_det == 2) {
-            const int sx = (lv.w + StreamGeo<2>::UX - 1) / StreamGeo<2>::UX;
-            k_detector_stream<2><<<dim3(sx * n_seg, 1, L.batch), 32, 0, L.stream>>>(ls, img_px, px, py, pd, mk, (size_t)P.dev.mask_words, p, sx, n_seg, RL);
-        } else if (lv.s_det == 3) {
-            const int sx = (lv.w + StreamGeo<3>::UX - 1) / StreamGeo<3>::UX;
-            k_detector_stream<3><<<dim3(sx * n_seg, 1, L.batch), 32, 0, L.stream>>>(ls, img_px, px, py, pd, mk, (size_t)P.dev.mask_words, p, sx, n_seg, RL);
-        } else {
-            const int sx = (lv.w + StreamGeo<4>::UX - 1) / StreamGeo<4>::UX;
-            k_detector_stream<4><<<dim3(sx * n_seg, 1, L.batch), 32, 0, L.stream>>>(ls, img_px, px, py, pd, mk, (size_t)P.dev.mask_words, p, sx, n_seg, RL);
-        }
+        auto go = [&](auto s_tag) {
+            constexpr int S = decltype(s_tag)::value;
+            const int sx = (lv.w + StreamGeo<S>::UX - 1) / StreamGeo<S>::UX;
+            k_detector_stream<S><<<dim3(sx * n_seg, 1, L.batch), 32, 0, L.stream>>>(ls, img_px, px, py, pd, mk, (size_t)P.dev.mask_words, p, sx, n_seg, RL);
+        };
+        if (lv.s_det == 2) go(std::integral_constant<int, 2>{});
+        else if (lv.s_det == 3) go(std::integral_constant<int, 3>{});
+        else go(std::integral_constant<int, 4>{});
         return 1;
     }
     if (fast) {
