@@ -462,6 +462,7 @@ __device__ __forceinline__ void det_store_rows(const DetStreamCtx<S>& k, float* 
 struct DetSteadyPtrs {
     float *px, *py, *pd;
     unsigned int* pm;
+    bool st1, st2, cd;  // this step's Lx/Ly row, Ldet row, candidate row belong to the segment (warp-uniform)
 };
 
 template <int S, bool STEADY, bool BORDER>
@@ -500,7 +501,7 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
         R.ly[2] = (n * b_m.z + wn * b_0.z) + n * R.bo[2];
         R.ly[3] = (n * b_m.w + wn * b_0.w) + n * R.bo[3];
         if (STEADY) {
-            if (k.xout) {
+            if (k.xout && sp.st1) {
                 st4(sp.px, make_float4(R.lx[0], R.lx[1], R.lx[2], R.lx[3]));
                 st4(sp.py, make_float4(R.ly[0], R.ly[1], R.ly[2], R.ly[3]));
             }
@@ -547,7 +548,7 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
             R.det_p[j] = ((lxx * lyy) - (lxy * lxy)) * k.quat;  // detector_response.rs:52
         }
         if (STEADY) {
-            if (k.xout) st4(sp.pd, make_float4(R.det_p[0], R.det_p[1], R.det_p[2], R.det_p[3]));
+            if (k.xout && sp.st2) st4(sp.pd, make_float4(R.det_p[0], R.det_p[1], R.det_p[2], R.det_p[3]));
         } else {
             det_store_rows<S>(k, k.od, o2, R.det_p);
         }
@@ -564,7 +565,7 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
         ring[4][s1][lane] = make_float4(R.dd[0], R.dd[1], R.dd[2], R.dd[3]);
     }
     // ---- candidates of row o3 = o2 - 1: threshold + strict 4-neighbour maximum + is_out
-    if (STEADY || (o3 >= k.Ya && o3 < k.Yb && o3 >= k.ymin && o3 <= k.ymax)) {
+    if (STEADY ? sp.cd : (o3 >= k.Ya && o3 < k.Yb && o3 >= k.ymin && o3 <= k.ymax)) {
         const float left = __shfl_up_sync(FULL, R.det_0[3], 1), right = __shfl_down_sync(FULL, R.det_0[0], 1);
         unsigned int nib = 0;
 #pragma unroll
@@ -615,11 +616,16 @@ __device__ __forceinline__ void det_stream_run(const DetStreamCtx<S>& k, float4 
     request_row(c_begin + 1);
     request_row(c_begin + 2);
     // rows [c_lo, c_hi] are steady (see det_stream_step); the others run the fully guarded step
-    const int c_lo = max(max(4 * S, k.Ya + 2 * S + 1), k.ymin + 2 * S + 1);
-    const int c_hi = min(min(k.yhi - 3, k.Yb - 1 + S), k.ymax + 2 * S + 1);
+    // (a segment's warm-up rows and the rows outside the candidate band are steady rows with their stores and the
+    // candidate test switched off by three warp-uniform flags: the guarded step costs ~4x a steady one, and with
+    // the flags only the 3S rows at the top and the 3S+4 rows at the bottom of the IMAGE still take it)
+    const int c_lo = max(4 * S, c_begin);
+    const int c_hi = min(k.yhi - 3, c_end);
+    const int lo3 = max(k.Ya, k.ymin), hi3 = min(k.Yb - 1, k.ymax);
+    const unsigned int seg_rows = (unsigned int)(k.Yb - k.Ya), cand_rows = hi3 >= lo3 ? (unsigned int)(hi3 - lo3 + 1) : 0u;
     int c = c_begin;
     const int no_slots[2] = {0, 0};
-    const DetSteadyPtrs no_ptrs = {nullptr, nullptr, nullptr, nullptr};
+    const DetSteadyPtrs no_ptrs = {nullptr, nullptr, nullptr, nullptr, false, false, false};
     auto generic_until = [&](int stop) {  // rows c .. stop-1
         for (; c < stop; c++) {
             request_row(c + 3);
@@ -648,6 +654,9 @@ __device__ __forceinline__ void det_stream_run(const DetStreamCtx<S>& k, float4 
             pl += k.W;
             cp_async_wait3();
             const float4 Lc = lq[c & 3][lane];
+            sp.st1 = (unsigned int)(c - S - k.Ya) < seg_rows;
+            sp.st2 = (unsigned int)(c - 2 * S - k.Ya) < seg_rows;
+            sp.cd = (unsigned int)(c - 2 * S - 1 - lo3) < cand_rows;
             det_stream_step<S, true, BORDER>(k, R, ring, c, Lc, sl, sp);
             advance();
             sp.px += k.W;
@@ -866,7 +875,15 @@ int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level)
     static const bool force_tile = getenv("AKZ_DETECTOR_TILE") != nullptr;  // A/B switch for profiling
     const bool stream = fast && !force_tile && lv.ymin >= lv.s_det + 1 && lv.ymax <= lv.h - 2 - lv.s_det && lv.h >= 4 * lv.s_det + 4;
     if (stream) {
-        const int RL = lv.h >= 512 ? 128 : (lv.h >= 256 ? 64 : 32);
+        // segment height: every segment re-runs 4S+2 warm-up rows, so take the tallest one that still gives the GPU a
+        // few waves of one-warp blocks (AKZ_DET_RL overrides, for profiling)
+        static const int rl_env = getenv("AKZ_DET_RL") ? atoi(getenv("AKZ_DET_RL")) : 0;
+        int RL = 256;
+        {
+            const int sx128 = (lv.w + 103) / 104;
+            while (RL > 32 && (long long)sx128 * std::max(1, (lv.h - 1 - lv.s_det) / RL) * L.batch < 148LL * 16 * 3) RL >>= 1;
+        }
+        if (rl_env > 0) RL = rl_env;
         const int n_seg = std::max(1, (lv.h - 1 - lv.s_det) / RL);
         float* px = B.Lx + off;
         float* py = B.Ly + off;

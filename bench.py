@@ -360,7 +360,7 @@ def run_extract(args):
     chunks_px = 0.0  # FED: pixels x launches (each launch reads Lt+Lflow, writes Lt = 12 B/px)
     for o, ns in enumerate(([3, 3, 4], [4, 5, 6, 7], [8, 10, 12, 14], [17, 20, 24, 29])):
         for nsteps in ns:
-            chunks_px += (px / 4 ** o) * ((nsteps + 7) // 8)  # k_fed runs up to 8 steps per launch
+            chunks_px += (px / 4 ** o) * ((nsteps + 3) // 4)  # k_fed_pp runs up to 4 steps per launch
     alg = {  # algorithmic HBM bytes per image of each stage as implemented
         "fed": 12.0 * chunks_px,
         "detector": 16.0 * sum_px,

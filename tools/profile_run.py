@@ -34,7 +34,11 @@ def main():
     import np_restatement as R
     eng = A.Engine(0, args.width, args.height, max(1, args.images))
     if not args.no_extract:
-        uniq = [R.natural_image(args.height, args.width, 1000 + i) for i in range(min(args.unique, args.images))]
+        cache = os.path.join(ROOT, "gpurun_out", "_ab_imgs_%dx%d_%d.npy" % (args.width, args.height, args.unique))
+        if os.path.exists(cache):  # written by tools/stage_ab.py: skips ~10 s of image synthesis per image
+            uniq = list(np.load(cache))[:max(1, min(args.unique, args.images))]
+        else:
+            uniq = [R.natural_image(args.height, args.width, 1000 + i) for i in range(min(args.unique, args.images))]
         imgs = [uniq[i % len(uniq)] for i in range(args.images)]
         for _ in range(args.runs):
             fs = eng.extract_batch_u8(imgs)
