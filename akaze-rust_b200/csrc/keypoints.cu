@@ -542,43 +542,63 @@ k_orientation(const PlanDev* __restrict__ plan, const float* __restrict__ lx_pla
         const float xf = ptx / ratio, yf = pty / ratio;
         const float* Lx = lx_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
         const float* Ly = ly_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
-        float rx[109], ry[109];
-        int idx = 0;
+        // The 109 samples sit on an 11 x 11 lattice (|a|, |b| <= 5: a*a + b*b < 36 excludes +-6), so only 11 column and 11
+        // row coordinates are rounded and range-checked (a column/row is used by at least the sample on the other axis'
+        // centre line, so "any of the 11 out of range" is exactly "any sample out of range").
+        int ixs[11], rows[11];
         bool oob = false;
-        for (int a = -6; a <= 6; a++)
-            for (int b = -6; b <= 6; b++)
-                if (a * a + b * b < 36) {
-                    int iy = (int)roundf(yf + (float)b * s);
-                    int ix = (int)roundf(xf + (float)a * s);
-                    if (ix < 0 || iy < 0 || ix >= lv.w || iy >= lv.h) {
-                        oob = true;
-                        ix = min(max(ix, 0), lv.w - 1);
-                        iy = min(max(iy, 0), lv.h - 1);
+#pragma unroll
+        for (int t = 0; t < 11; t++) {
+            int ix = (int)roundf(xf + (float)(t - 5) * s);
+            int iy = (int)roundf(yf + (float)(t - 5) * s);
+            if (ix < 0 || iy < 0 || ix >= lv.w || iy >= lv.h) {
+                oob = true;
+                ix = min(max(ix, 0), lv.w - 1);
+                iy = min(max(iy, 0), lv.h - 1);
+            }
+            ixs[t] = ix;
+            rows[t] = iy * lv.w;
+        }
+        // A sample takes part iff res_y > 0; the others are replaced by +0.0, which leaves a running f32 sum unchanged
+        // (the sums start at +0.0 and can never become -0.0), so the accumulation below needs no per-sample test.
+        float rx[109], ry[109];
+        {
+            int idx = 0;
+#pragma unroll
+            for (int a = -5; a <= 5; a++)
+#pragma unroll
+                for (int b = -5; b <= 5; b++)
+                    if (a * a + b * b < 36) {
+                        const int at = rows[b + 5] + ixs[a + 5];
+                        const float gw = c_gauss25[a < 0 ? -a : a][b < 0 ? -b : b];
+                        const float vx = gw * Lx[at], vy = gw * Ly[at];
+                        const bool in = vy > 0.0f;
+                        rx[idx] = in ? vx : 0.0f;
+                        ry[idx] = in ? vy : 0.0f;
+                        idx++;
                     }
-                    const int ia = a < 0 ? -a : a, ib = b < 0 ? -b : b;
-                    const float gw = c_gauss25[ia][ib];
-                    rx[idx] = gw * Lx[(size_t)iy * lv.w + ix];
-                    ry[idx] = gw * Ly[(size_t)iy * lv.w + ix];
-                    idx++;
-                }
-        float sum_x = 0.0f, sum_y = 0.0f, maxv = 0.0f, angle = 0.0f;
-        unsigned long long wm = plan->orient_window_mask;
-        for (int w = 0; w < plan->n_orient_windows; w++, wm >>= 1) {
-            if (wm & 1ull) {
-                for (int k = 0; k < 109; k++)
-                    if (ry[k] > 0.0f) {
-                        sum_x = sum_x + rx[k];
-                        sum_y = sum_y + ry[k];
-                    }
+        }
+        float sum_x = 0.0f, sum_y = 0.0f, maxv = 0.0f, best_x = 0.0f, best_y = 0.0f;
+        bool found = false;
+        // windows that do not contain pi/4 leave the sums, hence val, unchanged: only the others can raise the maximum
+        const int n_active = __popcll(plan->orient_window_mask & ((plan->n_orient_windows >= 64) ? ~0ull : ((1ull << plan->n_orient_windows) - 1ull)));
+        for (int w = 0; w < n_active; w++) {
+#pragma unroll
+            for (int k = 0; k < 109; k++) {
+                sum_x = sum_x + rx[k];
+                sum_y = sum_y + ry[k];
             }
             const float val = sum_x * sum_x + sum_y * sum_y;
             if (val > maxv) {
                 maxv = val;
-                // f32::atan2 -> libm atan2f; evaluated in f64 and rounded once (correctly rounded
-                // except for vanishingly rare double-rounding cases)
-                angle = (float)atan2((double)sum_y, (double)sum_x);
+                best_x = sum_x;
+                best_y = sum_y;
+                found = true;
             }
         }
+        // f32::atan2 -> libm atan2f; evaluated in f64 and rounded once (correctly rounded except for vanishingly rare
+        // double-rounding cases), once, for the window that won
+        const float angle = found ? (float)atan2((double)best_y, (double)best_x) : 0.0f;
         akz_keypoint kp;
         kp.x = ptx;
         kp.y = pty;
