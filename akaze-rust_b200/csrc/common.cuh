@@ -150,6 +150,7 @@ int launch_prep(const Launch& L, const Plan& P, const Buffers& B, int level);
 int launch_fed(const Launch& L, const Plan& P, const Buffers& B, int level);
 // detector.cu
 cudaError_t init_detector_attributes();
+cudaError_t init_scale_space_attributes();
 int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level);
 int launch_compact(const Launch& L, const Plan& P, const Buffers& B);
 // keypoints.cu

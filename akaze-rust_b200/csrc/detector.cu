@@ -839,6 +839,23 @@ cudaError_t init_detector_attributes() {
     const int pw = DT + 2 * (2 * kMaxDetScale + 1);
     cudaError_t e = cudaFuncSetAttribute(k_detector, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * pw * pw * (int)sizeof(float));
     if (e != cudaSuccess) return e;
+    // all pipeline kernels ask for the largest shared-memory carveout: an SM cannot change its L1/shared split while any
+    // block is resident, and the cache pass (k_dedup_smem, one long-lived warp per image on every SM) used to pin the
+    // small split chosen for it, which cut the streaming kernels' resident warps for as long as it ran
+    if (getenv("AKZ_NO_CARVEOUT") == nullptr) {
+        e = cudaFuncSetAttribute(k_detector_stream<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_detector_stream<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_detector_stream<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_rowcount, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_rowscan, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_scatter, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+    }
     e = cudaFuncSetAttribute(k_detector_fast<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, DetGeo<2>::FLOATS * (int)sizeof(float));
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_detector_fast<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, DetGeo<3>::FLOATS * (int)sizeof(float));

@@ -12,6 +12,8 @@
 // drop). That semantics is kept exactly: one warp walks one image's ordered candidate list; the linear
 // cache scan is replaced by a spatial hash (two grids, one per class parity, since only classes L and
 // L-1 can match) whose cells are searched in parallel by the lanes for the LOWEST matching slot.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace akz {
@@ -785,7 +787,13 @@ k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plan
 
 }  // namespace
 
-cudaError_t init_keypoint_attributes() { return cudaSuccess; }
+cudaError_t init_keypoint_attributes() {
+    // see init_detector_attributes: the cache pass must not pin a small shared-memory carveout on the SMs it lives on
+    if (getenv("AKZ_NO_CARVEOUT") != nullptr) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k_dedup_smem, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_dedup, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
 
 size_t dedup_pool_bytes() { return sizeof(DedupPool); }
 
