@@ -663,6 +663,9 @@ __device__ __forceinline__ void desc_cell_sums_rt(const float* smp, float* val, 
     }
 }
 
+// DEF: Config::default() descriptor geometry (pattern 10, 3 channels) as compile-time constants -- the divisions by the
+// lattice edge and the channel count fold into multiplies (they were 17 % of the kernel's instructions)
+template <bool DEF>
 __global__ void __launch_bounds__(32 * kDescWarps)
 k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plane, const float* __restrict__ lx_plane,
              const float* __restrict__ ly_plane, int batch, unsigned int kp_cap, const akz_keypoint* __restrict__ kps,
@@ -674,12 +677,12 @@ k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plan
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const unsigned int n = min(n_kp[img], kp_cap);
     const int warps = (blockDim.x >> 5) * gridDim.x;
-    const int nch = plan->channels;
-    const int pattern = plan->pattern_size;
+    const int nch = DEF ? 3 : plan->channels;
+    const int pattern = DEF ? 10 : plan->pattern_size;
     // sample_size per grid level: ceil(pattern * {1, 2/3, 1/2}) in f32 (descriptors.rs:50,61)
     const float pf = (float)pattern;
     const int st0 = (int)ceilf(pf * 1.0f), st1 = (int)ceilf(pf * (2.0f / 3.0f)), st2 = (int)ceilf(pf * (1.0f / 2.0f));
-    const int M = max(2 * st0, max(3 * st1, 4 * st2));  // <= kDescM (validated on the host)
+    const int M = DEF ? kDescM : max(2 * st0, max(3 * st1, 4 * st2));  // <= kDescM (validated on the host)
     const int MM = M * M;
     const int nbits = 162 * nch;
     {   // bit -> (i, j) table, identical for every keypoint
@@ -724,39 +727,58 @@ k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plan
         bool oob = false;
         // ---- phase 1: the M x M lattice; fast lane index runs along the lattice axis closest to image x
         const bool k_fast = fabsf(co) >= fabsf(si);
-        for (int s0 = 0; s0 < MM; s0 += 32) {
-            const int s = s0 + lane;
-            if (s < MM) {
-                const int a = s / M, b = s - a * M;
-                const int kk = k_fast ? b : a, ll = k_fast ? a : b;
-                const float lf = (float)(ll - pattern) + 0.5f, kf = (float)(kk - pattern) + 0.5f;
-                const float sample_y = yf + (lf * co * scale + kf * si * scale);
-                const float sample_x = xf + (-lf * si * scale + kf * co * scale);
-                int y1 = (int)roundf(sample_y), x1 = (int)roundf(sample_x);
-                if (x1 < 0 || y1 < 0 || x1 >= W || y1 >= H) {
-                    oob = true;
-                    x1 = min(max(x1, 0), W - 1);
-                    y1 = min(max(y1, 0), H - 1);
-                }
-                const size_t at = (size_t)y1 * W + x1;
-                const int so = kk * M + ll;
-                smp[so] = Lt[at];
-                if (nch > 1) {
-                    const float rx = Lx[at], ry = Ly[at];
-                    if (nch == 2) {
-                        smp[kDescCS + so] = sqrtf(rx * rx + ry * ry);
-                    } else {
-                        const float rry = rx * co + ry * si;
-                        const float rrx = -rx * si + ry * co;
-                        smp[kDescCS + so] = rrx;
-                        smp[2 * kDescCS + so] = rry;
+        // two lattice points per lane and iteration: the six gathers are issued before the first of them is used
+        for (int s0 = 0; s0 < MM; s0 += 64) {
+            float v_t[2], v_x[2], v_y[2];
+            int so[2];
+            bool act[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int s = s0 + 32 * u + lane;
+                act[u] = s < MM;
+                so[u] = 0;
+                v_t[u] = v_x[u] = v_y[u] = 0.0f;
+                if (act[u]) {
+                    const int a = s / M, b = s - a * M;
+                    const int kk = k_fast ? b : a, ll = k_fast ? a : b;
+                    const float lf = (float)(ll - pattern) + 0.5f, kf = (float)(kk - pattern) + 0.5f;
+                    const float sample_y = yf + (lf * co * scale + kf * si * scale);
+                    const float sample_x = xf + (-lf * si * scale + kf * co * scale);
+                    int y1 = (int)roundf(sample_y), x1 = (int)roundf(sample_x);
+                    if (x1 < 0 || y1 < 0 || x1 >= W || y1 >= H) {
+                        oob = true;
+                        x1 = min(max(x1, 0), W - 1);
+                        y1 = min(max(y1, 0), H - 1);
+                    }
+                    const int at = y1 * W + x1;  // one level image is far below 2^31 pixels
+                    so[u] = kk * M + ll;
+                    v_t[u] = Lt[at];
+                    if (nch > 1) {
+                        v_x[u] = Lx[at];
+                        v_y[u] = Ly[at];
                     }
                 }
             }
+#pragma unroll
+            for (int u = 0; u < 2; u++)
+                if (act[u]) {
+                    smp[so[u]] = v_t[u];
+                    if (nch > 1) {
+                        const float rx = v_x[u], ry = v_y[u];
+                        if (nch == 2) {
+                            smp[kDescCS + so[u]] = sqrtf(rx * rx + ry * ry);
+                        } else {
+                            const float rry = rx * co + ry * si;
+                            const float rrx = -rx * si + ry * co;
+                            smp[kDescCS + so[u]] = rrx;
+                            smp[2 * kDescCS + so[u]] = rry;
+                        }
+                    }
+                }
         }
         __syncwarp();
         // ---- phase 2: sequential sums per (cell, channel); values of grid g start at cell_base(g) = 0, 4, 13
-        if (pattern == 10) {
+        if (DEF || pattern == 10) {
             desc_cell_sums<10, 2>(smp, val, M, nch, lane);
             desc_cell_sums<7, 3>(smp, val + 4 * 3, M, nch, lane);
             desc_cell_sums<5, 4>(smp, val + 13 * 3, M, nch, lane);
@@ -822,7 +844,10 @@ int launch_finalize(const Launch& L, const Plan& P, const Buffers& B) {
 
 int launch_descriptors(const Launch& L, const Plan& P, const Buffers& B) {
     dim3 g(32, L.batch);
-    k_descriptor<<<g, 256, 0, L.stream>>>(B.plan_dev, B.Lt, B.Lx, B.Ly, L.batch, L.kp_cap, B.kps, B.n_kp, B.desc, B.err_flags);
+    if (P.dev.channels == 3 && P.dev.pattern_size == 10)
+        k_descriptor<true><<<g, 256, 0, L.stream>>>(B.plan_dev, B.Lt, B.Lx, B.Ly, L.batch, L.kp_cap, B.kps, B.n_kp, B.desc, B.err_flags);
+    else
+        k_descriptor<false><<<g, 256, 0, L.stream>>>(B.plan_dev, B.Lt, B.Lx, B.Ly, L.batch, L.kp_cap, B.kps, B.n_kp, B.desc, B.err_flags);
     return 1;
 }
 
