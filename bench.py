@@ -17,6 +17,7 @@ Hamming matcher (configs[4]) instead, database sharded over ranks with an NCCL a
 so that arm runs the line-faithful C restatement in oracle/ (cpu_baseline.kind = "port").
 """
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -384,21 +385,22 @@ def run_extract(args):
     per_launch = st[dom][0] / max(1, st[dom][1])
     # measured DRAM traffic of the stage from the committed ncu capture, scaled to this run's average launch
     traffic, traffic_src = None, None
-    tp = os.path.join(ROOT, "profiles", "r1w_stage_traffic.json")
-    if os.path.exists(tp):
-        with open(tp) as fh:
+    tps = sorted(glob.glob(os.path.join(ROOT, "profiles", "*stage_traffic.json")))  # the newest capture (names sort by round tag)
+    if tps:
+        with open(tps[-1]) as fh:
             tj = json.load(fh)
         if dom in tj["stages"]:
             traffic = tj["stages"][dom]["dram_bytes_per_image"] * n_img / max(1, st[dom][1])
-            traffic_src = "profiles/r1w_stage_traffic.json (ncu --set full, dram__bytes_read+write, 4-image capture: part of the planes stays in L2)"
+            traffic_src = "profiles/%s (ncu --set full, dram__bytes_read+write summed over the stage, %d-image capture)" % (
+                os.path.basename(tps[-1]), tj.get("images_in_capture", 0))
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "avg_launch_ms": per_launch,
                 "algorithmic_bytes_per_launch": (alg[dom] * n_img / max(1, st[dom][1])) if dom in alg else None,
                 "algorithmic_bytes_per_image": alg.get(dom),
-                "note": "stage timed alone by CUDA events inside the library (serialised timing pass); the stencil kernels are "
-                        "instruction-issue bound, not DRAM bound (profiles/r1w_ncu_summary.csv), so frac is far below 1 by construction; "
-                        "fp32_ridge_frac is the fraction of the FP32 non-FMA peak (SURVEY 8d: 724 flop per input pixel, 37.2 TFLOP/s) the "
-                        "stencil stages reach",
+                "note": "stage timed alone by CUDA events inside the library (serialised timing pass). The streaming detector is bound by "
+                        "the shared-memory/LSU pipe (82 % of its peak at full load, profiles/r1z_ncu_fullload.txt), its DRAM traffic equals "
+                        "the algorithmic bytes; fp32_ridge_frac is the fraction of the FP32 non-FMA peak (SURVEY 8d: 724 flop per input "
+                        "pixel, 37.2 TFLOP/s) the stencil stages reach",
                 "fp32_ridge_frac": (724.0 * px / 37.2e12) / (1e-3 * sum(st[k][0] for k in ("level0", "contrast", "prep", "fed", "detector") if k in st) / n_img)}
     pipe_ach = ALG_BYTES_PER_PX * px * (n_img * args.steps) / (ms / 1000.0) / 1e9
     roofline_pipeline = {"bound": "hbm", "achieved": pipe_ach, "peak": peak, "unit": "GB/s", "frac": pipe_ach / peak,

@@ -1,10 +1,9 @@
 #!/bin/bash
-# One GPU-box visit: parity tests, both bench workloads, the ncu launch list and ncu captures.
-# usage: tools/gpu_round.sh <tag> [what...]   what in: tests extract match launches full src   (default: all)
-# gpurun copies back at most 64 MiB of gpurun_out/, so .ncu-rep files are converted to CSV on the box and
-# only small reports are kept.
+# One GPU-box visit: parity tests, both bench workloads, the ncu launch list and the full ncu capture.
+# usage: tools/gpu_round.sh <tag> [what...]   what in: tests extract match launches full   (default: all)
+# gpurun copies back at most 64 MiB of gpurun_out/, so the big .ncu-rep stays on the box and only its CSV export returns.
 tag=${1:-x}; shift
-what=${*:-tests extract match launches full src srcmatch}
+what=${*:-tests extract match launches full}
 mkdir -p gpurun_out
 has() { [[ " $what " == *" $1 "* ]]; }
 if has tests; then
@@ -25,20 +24,14 @@ fi
 if has match; then
   timeout 600 python bench.py --workload match > gpurun_out/${tag}_bench_match.json 2> gpurun_out/${tag}_bench_match.err; tail -c 1200 gpurun_out/${tag}_bench_match.json; tail -5 gpurun_out/${tag}_bench_match.err
 fi
+# the profiling runs reuse the synthetic images cached by tools/stage_ab.py (image synthesis takes ~10 s per image)
+if has launches || has full; then python tools/stage_ab.py --images 8 "" > /dev/null 2>&1; fi
 if has launches; then
-  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ --csv --log-file gpurun_out/${tag}_launches.csv python tools/profile_run.py --images 32 --match 65536 > gpurun_out/${tag}_launches.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 1 --warmup 1 --images 256 --unique 4 --no-e2e --no-cpu > gpurun_out/${tag}_launches.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_match --csv --log-file gpurun_out/${tag}_launches_match.csv python tools/profile_run.py --no-extract --match 65536 >> gpurun_out/${tag}_launches.log 2>&1
 fi
 if has full; then
-  timeout 900 ncu --set full --clock-control none -k regex:k_ -c 260 -o /tmp/${tag}_full python tools/profile_run.py --images 4 --match 32768 > gpurun_out/${tag}_full.log 2>&1
+  timeout 900 ncu --set full --clock-control none -k regex:k_ -c 400 -o /tmp/${tag}_full python tools/profile_run.py --images 64 --match 32768 > gpurun_out/${tag}_full.log 2>&1
   ncu -i /tmp/${tag}_full.ncu-rep --page raw --csv > gpurun_out/${tag}_full_raw.csv 2>> gpurun_out/${tag}_full.log
-fi
-if has src; then
-  timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:"${NCU_SRC_REGEX:-k_detector_stream}" -c ${NCU_SRC_COUNT:-4} -o gpurun_out/${tag}_src python tools/profile_run.py --images ${NCU_SRC_IMAGES:-8} > gpurun_out/${tag}_src.log 2>&1
-  ls -la gpurun_out/${tag}_src.ncu-rep
-  if [ $(stat -c %s gpurun_out/${tag}_src.ncu-rep 2>/dev/null || echo 0) -gt 30000000 ]; then rm -f gpurun_out/${tag}_src.ncu-rep; fi
-fi
-if has srcmatch; then
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_match_tc -c 1 -o gpurun_out/${tag}_srcmatch python tools/profile_run.py --no-extract --match 131072 > gpurun_out/${tag}_srcmatch.log 2>&1
-  ls -la gpurun_out/${tag}_srcmatch.ncu-rep
 fi
 du -sh gpurun_out
