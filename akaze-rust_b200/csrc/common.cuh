@@ -100,6 +100,7 @@ struct Buffers {
     float* in_f32 = nullptr;
     // contrast
     unsigned long long* hmax_bits = nullptr;  // [B] f64 bits (values >= 0 order like u64)
+    double* contrast_thr = nullptr;           // [B][kMaxBins + 1] smallest squared gradient magnitude that falls into bin b
     unsigned int* hist = nullptr;             // [B][n_bins]
     double* kcontrast = nullptr;              // [B][kMaxLevels] contrast factor per level
     // candidates
