@@ -457,6 +457,79 @@ __device__ __forceinline__ void det_store_rows(const DetStreamCtx<S>& k, float* 
         for (int r = max(k.yhi + 1, k.Ya); r < min(k.H, k.Yb); r++) st4(plane + (size_t)r * k.W + k.x0, q);
 }
 
+// ---- where the five per-lane rings (A, Bo, C, E, D; 2S rows of one float4 per lane each) live -------------------------
+// RingSmem: shared memory, one warp per block (the original layout). RingTmem: TENSOR MEMORY used as a per-lane delay
+// line -- each warp of a four-warp CTA owns its quarter of the 128 TMEM lanes, a ring row is four 32-bit columns, and
+// tcgen05.ld/st.32x32b.x4 moves exactly the float4-per-thread shape the rings need. The detector is bound by the
+// shared-memory/LSU pipe (82 % of its peak, profiles/r1z_ncu_fullload.txt); the ring accesses are 52 of its ~92 pipe
+// cycles per row, and tools/microbench/tmem_ring.cu measured the same 8-load/5-store mix at 382 B/clk/SM in TMEM
+// against 97 in shared memory. For S = 4 the rings need 160 columns; ring A (one read, one write per row) stays in
+// shared memory so that 128 columns suffice and four CTAs (16 warps) fit an SM's 512 columns for every S.
+template <int S>
+struct RingSmem {
+    float4 (*ring)[StreamGeo<S>::D][32];
+    int lane;
+    // a ring row is named by a handle: here simply the slot index
+    __device__ __forceinline__ int handle(int slot) const { return slot; }
+    __device__ __forceinline__ int next(int h) const { return (h + 1 == StreamGeo<S>::D) ? 0 : h + 1; }
+    template <int A>
+    __device__ __forceinline__ float4 load(int h) const { return ring[A][h][lane]; }
+    template <int A>
+    __device__ __forceinline__ void store(int h, const float4& v) const { ring[A][h][lane] = v; }
+    __device__ __forceinline__ void row_begin() const {}
+    __device__ __forceinline__ void fence3(float4&, float4&, float4&) const {}
+    __device__ __forceinline__ void fence5(float4&, float4&, float4&, float4&, float4&) const {}
+};
+
+template <int S>
+struct RingTmem {
+    static constexpr int D = StreamGeo<S>::D;
+    static constexpr bool A_IN_SMEM = (S == 4);
+    static constexpr int COLS = 128;  // allocation (power of two >= 32): 5 * 2S * 4 = 80 / 120 columns, or 4 * 8 * 4 = 128 for S = 4
+    unsigned int base;                // TMEM address: this warp's first lane, first column of the CTA's allocation
+    float4 (*ring_a)[32];             // S = 4 only: ring A of this warp in shared memory
+    int lane;
+    // a ring row is named by a handle = 4 * slot (its column offset inside one array); the array's columns and the warp's
+    // TMEM base are compile-time / loop-invariant, so a steady row spends two adds on addressing instead of one per access
+    __device__ __forceinline__ int handle(int slot) const { return 4 * slot; }
+    __device__ __forceinline__ int next(int h) const { return (h + 4 == 4 * D) ? 0 : h + 4; }
+    template <int A>
+    __device__ __forceinline__ unsigned int addr(int h) const {
+        return base + (unsigned int)((A_IN_SMEM ? A - 1 : A) * D * 4) + (unsigned int)h;
+    }
+    template <int A>
+    __device__ __forceinline__ float4 load(int h) const {
+        if (A_IN_SMEM && A == 0) return ring_a[h >> 2][lane];
+        unsigned int r0, r1, r2, r3;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr<A>(h)) : "memory");
+        return make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3));
+    }
+    template <int A>
+    __device__ __forceinline__ void store(int h, const float4& v) const {
+        if (A_IN_SMEM && A == 0) {
+            ring_a[h >> 2][lane] = v;
+            return;
+        }
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr<A>(h)), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)) : "memory");
+    }
+    // a row's stores are read again S rows later at the earliest: one wait per row covers them
+    __device__ __forceinline__ void row_begin() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+    // the loaded registers are in/out operands of the wait, so that no use of them can be scheduled above it
+    __device__ __forceinline__ void fence3(float4& a, float4& b, float4& c) const {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w), "+f"(b.x), "+f"(b.y), "+f"(b.z), "+f"(b.w), "+f"(c.x), "+f"(c.y), "+f"(c.z), "+f"(c.w)
+                     :
+                     : "memory");
+    }
+    __device__ __forceinline__ void fence5(float4& a, float4& b, float4& c, float4& d, float4& e) const {
+        asm volatile("tcgen05.wait::ld.sync.aligned;"
+                     : "+f"(a.x), "+f"(a.y), "+f"(a.z), "+f"(a.w), "+f"(b.x), "+f"(b.y), "+f"(b.z), "+f"(b.w), "+f"(c.x), "+f"(c.y), "+f"(c.z), "+f"(c.w),
+                       "+f"(d.x), "+f"(d.y), "+f"(d.z), "+f"(d.w), "+f"(e.x), "+f"(e.y), "+f"(e.z), "+f"(e.w)
+                     :
+                     : "memory");
+    }
+};
+
 // where the steady rows store: Lx/Ly row c-S, Ldet row c-2S, mask word of row c-2S-1 (advanced one row per step by the
 // caller, so the steady body does no 64-bit index arithmetic)
 struct DetSteadyPtrs {
@@ -465,8 +538,8 @@ struct DetSteadyPtrs {
     bool st1, st2, cd;  // this step's Lx/Ly row, Ldet row, candidate row belong to the segment (warp-uniform)
 };
 
-template <int S, bool STEADY, bool BORDER>
-__device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStreamRegs<S>& R, float4 (*ring)[StreamGeo<S>::D][32],
+template <int S, bool STEADY, bool BORDER, class RG>
+__device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStreamRegs<S>& R, const RG& rg,
                                                 int c, const float4& Lc, const int (&sl)[2], const DetSteadyPtrs& sp) {
     using G = StreamGeo<S>;
     constexpr unsigned int FULL = 0xffffffffu;
@@ -474,8 +547,8 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
     const float n = k.n, wn = k.wn;
     const int lane = k.lane;
     // ring slots of rows c, c-S, c-2S, c-3S
-    const int s0 = STEADY ? sl[0] : (c % D);
-    const int s1 = STEADY ? sl[1] : ((c - S) % D);
+    const int s0 = STEADY ? sl[0] : rg.handle(c % D);
+    const int s1 = STEADY ? sl[1] : rg.handle((c - S) % D);
     const int o1 = c - S, o2 = c - 2 * S, o3 = o2 - 1;
     // ---- A = H_main(Lsmooth), Bo = H_off(Lsmooth), row c (rows beyond yhi keep the registers of row yhi)
     if (STEADY || c <= k.yhi) {
@@ -493,8 +566,9 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
     // ---- Lx = V_off(A), Ly = V_main(Bo), row o1 = c - S
     const bool row1 = STEADY || (o1 >= k.ylo && o1 <= k.yhi);
     if (row1) {
-        const int rm = STEADY ? sl[0] : (max(o1 - S, k.ylo) % D);  // row c - 2S shares the slot of row c
-        const float4 a_m = ring[0][rm][lane], b_m = ring[1][rm][lane], b_0 = ring[1][s1][lane];
+        const int rm = STEADY ? sl[0] : rg.handle(max(o1 - S, k.ylo) % D);  // row c - 2S shares the slot of row c
+        float4 a_m = rg.template load<0>(rm), b_m = rg.template load<1>(rm), b_0 = rg.template load<1>(s1);
+        rg.fence3(a_m, b_m, b_0);
         R.lx[0] = R.a[0] - a_m.x; R.lx[1] = R.a[1] - a_m.y; R.lx[2] = R.a[2] - a_m.z; R.lx[3] = R.a[3] - a_m.w;
         R.ly[0] = (n * b_m.x + wn * b_0.x) + n * R.bo[0];
         R.ly[1] = (n * b_m.y + wn * b_0.y) + n * R.bo[1];
@@ -511,8 +585,8 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
         }
     }
     if (STEADY || c <= k.yhi) {  // after the reads above: row c may reuse the slot of row c - 2S
-        ring[0][s0][lane] = make_float4(R.a[0], R.a[1], R.a[2], R.a[3]);
-        ring[1][s0][lane] = make_float4(R.bo[0], R.bo[1], R.bo[2], R.bo[3]);
+        rg.template store<0>(s0, make_float4(R.a[0], R.a[1], R.a[2], R.a[3]));
+        rg.template store<1>(s0, make_float4(R.bo[0], R.bo[1], R.bo[2], R.bo[3]));
     }
     // ---- C = H_main(Lx), E = H_off(Lx), D = H_off(Ly), row o1
     if (row1) {
@@ -532,10 +606,11 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
     }
     // ---- Lxx = V_off(C), Lxy = V_main(E), Lyy = V_main(D), Ldet, row o2 = c - 2S
     if (STEADY || (o2 >= k.ylo && o2 <= k.yhi)) {
-        const int rm = STEADY ? sl[1] : (max(o2 - S, k.ylo) % D);  // row c - 3S shares the slot of row c - S
-        const int r0 = STEADY ? sl[0] : ((o2 + 2 * D) % D);
-        const float4 c_m = ring[2][rm][lane], e_m = ring[3][rm][lane], e_0 = ring[3][r0][lane];
-        const float4 d_m = ring[4][rm][lane], d_0 = ring[4][r0][lane];
+        const int rm = STEADY ? sl[1] : rg.handle(max(o2 - S, k.ylo) % D);  // row c - 3S shares the slot of row c - S
+        const int r0 = STEADY ? sl[0] : rg.handle((o2 + 2 * D) % D);
+        float4 c_m = rg.template load<2>(rm), e_m = rg.template load<3>(rm), e_0 = rg.template load<3>(r0);
+        float4 d_m = rg.template load<4>(rm), d_0 = rg.template load<4>(r0);
+        rg.fence5(c_m, e_m, e_0, d_m, d_0);
         const float cm[4] = {c_m.x, c_m.y, c_m.z, c_m.w}, em[4] = {e_m.x, e_m.y, e_m.z, e_m.w}, e0[4] = {e_0.x, e_0.y, e_0.z, e_0.w};
         const float dm[4] = {d_m.x, d_m.y, d_m.z, d_m.w}, d0[4] = {d_0.x, d_0.y, d_0.z, d_0.w};
 #pragma unroll
@@ -560,9 +635,9 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
         }
     }
     if (row1) {
-        ring[2][s1][lane] = make_float4(R.cc[0], R.cc[1], R.cc[2], R.cc[3]);
-        ring[3][s1][lane] = make_float4(R.ee[0], R.ee[1], R.ee[2], R.ee[3]);
-        ring[4][s1][lane] = make_float4(R.dd[0], R.dd[1], R.dd[2], R.dd[3]);
+        rg.template store<2>(s1, make_float4(R.cc[0], R.cc[1], R.cc[2], R.cc[3]));
+        rg.template store<3>(s1, make_float4(R.ee[0], R.ee[1], R.ee[2], R.ee[3]));
+        rg.template store<4>(s1, make_float4(R.dd[0], R.dd[1], R.dd[2], R.dd[3]));
     }
     // ---- candidates of row o3 = o2 - 1: threshold + strict 4-neighbour maximum + is_out
     if (STEADY ? sp.cd : (o3 >= k.Ya && o3 < k.Yb && o3 >= k.ymin && o3 <= k.ymax)) {
@@ -597,9 +672,8 @@ __device__ __forceinline__ void cp_async16(float4* smem_dst, const float* gsrc) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait3() { asm volatile("cp.async.wait_group 3;" ::: "memory"); }
 
-template <int S, bool BORDER>
-__device__ __forceinline__ void det_stream_run(const DetStreamCtx<S>& k, float4 (*ring)[StreamGeo<S>::D][32], float4 (*lq)[32], int c_begin,
-                                               int c_end) {
+template <int S, bool BORDER, class RG>
+__device__ __forceinline__ void det_stream_run(const DetStreamCtx<S>& k, const RG& rg, float4 (*lq)[32], int c_begin, int c_end) {
     using G = StreamGeo<S>;
     DetStreamRegs<S> R;
 #pragma unroll
@@ -631,12 +705,13 @@ __device__ __forceinline__ void det_stream_run(const DetStreamCtx<S>& k, float4 
             request_row(c + 3);
             cp_async_wait3();
             const float4 Lc = lq[c & 3][lane];
-            det_stream_step<S, false, BORDER>(k, R, ring, c, Lc, no_slots, no_ptrs);
+            rg.row_begin();
+            det_stream_step<S, false, BORDER>(k, R, rg, c, Lc, no_slots, no_ptrs);
         }
     };
     if (c_lo <= c_hi) {
         generic_until(max(c_lo, c_begin));
-        int sl[2] = {c % G::D, (c - S) % G::D};  // c >= 4S here
+        int sl[2] = {rg.handle(c % G::D), rg.handle((c - S) % G::D)};  // c >= 4S here
         const float* pl = k.L + (size_t)(c + 3) * k.W + k.x0;  // row c + 3 <= yhi
         DetSteadyPtrs sp;
         sp.px = k.ox + (ptrdiff_t)(c - S) * k.W + k.x0;
@@ -645,7 +720,7 @@ __device__ __forceinline__ void det_stream_run(const DetStreamCtx<S>& k, float4 
         sp.pm = k.m + (ptrdiff_t)(c - 2 * S - 1) * k.wpr + (k.x0 >> 5);
         auto advance = [&]() {
 #pragma unroll
-            for (int i = 0; i < 2; i++) sl[i] = (sl[i] + 1 == G::D) ? 0 : sl[i] + 1;
+            for (int i = 0; i < 2; i++) sl[i] = rg.next(sl[i]);
         };
 #pragma unroll 1
         for (; c <= c_hi; c++) {
@@ -657,7 +732,8 @@ __device__ __forceinline__ void det_stream_run(const DetStreamCtx<S>& k, float4 
             sp.st1 = (unsigned int)(c - S - k.Ya) < seg_rows;
             sp.st2 = (unsigned int)(c - 2 * S - k.Ya) < seg_rows;
             sp.cd = (unsigned int)(c - 2 * S - 1 - lo3) < cand_rows;
-            det_stream_step<S, true, BORDER>(k, R, ring, c, Lc, sl, sp);
+            rg.row_begin();
+            det_stream_step<S, true, BORDER>(k, R, rg, c, Lc, sl, sp);
             advance();
             sp.px += k.W;
             sp.py += k.W;
@@ -668,18 +744,13 @@ __device__ __forceinline__ void det_stream_run(const DetStreamCtx<S>& k, float4 
     generic_until(c_end + 1);
 }
 
+// strip `si`, segment `sj` of image `img` -> the per-warp context
 template <int S>
-__global__ void __launch_bounds__(32)
-k_detector_stream(const float* __restrict__ lsmooth, size_t img_px, float* __restrict__ oLx, float* __restrict__ oLy,
-                  float* __restrict__ oLdet, unsigned int* __restrict__ mask, size_t mask_img_words, DetParams p, int strips_x,
-                  int n_seg, int RL) {
+__device__ __forceinline__ void det_stream_ctx(DetStreamCtx<S>& k, const DetParams& p, int si, int sj, int img, int n_seg, int RL,
+                                               const float* lsmooth, size_t img_px, float* oLx, float* oLy, float* oLdet,
+                                               unsigned int* mask, size_t mask_img_words) {
     using G = StreamGeo<S>;
-    __shared__ float4 ring[5][G::D][32];  // A, Bo, C, E, D
-    __shared__ float4 lq[4][32];          // cp.async queue of Lsmooth rows
-    DetStreamCtx<S> k;
-    k.lane = threadIdx.x;
-    const int si = blockIdx.x % strips_x, sj = blockIdx.x / strips_x;
-    const int img = blockIdx.z;
+    k.lane = threadIdx.x & 31;
     k.W = p.W;
     k.H = p.H;
     k.n = p.n;
@@ -711,11 +782,63 @@ k_detector_stream(const float* __restrict__ lsmooth, size_t img_px, float* __res
     k.oy = oLy + ibase;
     k.od = oLdet + ibase;
     k.m = mask + (size_t)img * mask_img_words;
+}
+
+template <int S>
+__global__ void __launch_bounds__(32)
+k_detector_stream(const float* __restrict__ lsmooth, size_t img_px, float* __restrict__ oLx, float* __restrict__ oLy,
+                  float* __restrict__ oLdet, unsigned int* __restrict__ mask, size_t mask_img_words, DetParams p, int strips_x,
+                  int n_seg, int RL) {
+    using G = StreamGeo<S>;
+    __shared__ float4 ring[5][G::D][32];  // A, Bo, C, E, D
+    __shared__ float4 lq[4][32];          // cp.async queue of Lsmooth rows
+    DetStreamCtx<S> k;
+    det_stream_ctx<S>(k, p, blockIdx.x % strips_x, blockIdx.x / strips_x, blockIdx.z, n_seg, RL, lsmooth, img_px, oLx, oLy, oLdet, mask,
+                      mask_img_words);
+    const RingSmem<S> rg{ring, k.lane};
     const int c_begin = max(k.ylo, k.Ya - 1 - 2 * S), c_end = k.Yb + 2 * S;
     if (k.has_l || k.has_r)
-        det_stream_run<S, true>(k, ring, lq, c_begin, c_end);
+        det_stream_run<S, true>(k, rg, lq, c_begin, c_end);
     else
-        det_stream_run<S, false>(k, ring, lq, c_begin, c_end);
+        det_stream_run<S, false>(k, rg, lq, c_begin, c_end);
+}
+
+// The same stream with the rings in tensor memory (RingTmem): four warps = four strips per CTA, 128 TMEM columns per CTA.
+constexpr int DT_WARPS = 4;
+template <int S>
+__global__ void __launch_bounds__(DT_WARPS * 32, 4)
+k_detector_tmem(const float* __restrict__ lsmooth, size_t img_px, float* __restrict__ oLx, float* __restrict__ oLy,
+                float* __restrict__ oLdet, unsigned int* __restrict__ mask, size_t mask_img_words, DetParams p, int strips_x,
+                int n_seg, int RL) {
+    using G = StreamGeo<S>;
+    using RT = RingTmem<S>;
+    __shared__ float4 lq[DT_WARPS][4][32];  // cp.async queues of Lsmooth rows
+    __shared__ float4 ring_a[RT::A_IN_SMEM ? DT_WARPS : 1][RT::A_IN_SMEM ? G::D : 1][32];
+    __shared__ unsigned int tmem_slot;
+    const int warp = threadIdx.x >> 5;
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned int)__cvta_generic_to_shared(&tmem_slot)), "r"((unsigned int)RT::COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int strip = blockIdx.x * DT_WARPS + warp;
+    if (strip < strips_x * n_seg) {  // surplus warps of the last CTA only take part in the barriers
+        DetStreamCtx<S> k;
+        det_stream_ctx<S>(k, p, strip % strips_x, strip / strips_x, blockIdx.z, n_seg, RL, lsmooth, img_px, oLx, oLy, oLdet, mask,
+                          mask_img_words);
+        const RT rg{tmem_slot + ((unsigned int)(warp * 32) << 16), ring_a[RT::A_IN_SMEM ? warp : 0], k.lane};
+        const int c_begin = max(k.ylo, k.Ya - 1 - 2 * S), c_end = k.Yb + 2 * S;
+        if (k.has_l || k.has_r)
+            det_stream_run<S, true>(k, rg, lq[warp], c_begin, c_end);
+        else
+            det_stream_run<S, false>(k, rg, lq[warp], c_begin, c_end);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"((unsigned int)RT::COLS) : "memory");
 }
 
 // ---- bitmask -> ordered list ------------------------------------------------------------------
@@ -901,14 +1024,23 @@ int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level)
             while (RL > 32 && (long long)sx128 * std::max(1, (lv.h - 1 - lv.s_det) / RL) * L.batch < 148LL * 16 * 3) RL >>= 1;
         }
         if (rl_env > 0) RL = rl_env;
-        const int n_seg = std::max(1, (lv.h - 1 - lv.s_det) / RL);
+        // equal-height segments (the last one used to take the remainder: 312 rows against 256 at 1080p, and a CTA of the
+        // tensor-memory kernel waits for its slowest warp)
+        int n_seg = std::max(1, (lv.h + RL / 2) / RL);
+        RL = (lv.h + n_seg - 1) / n_seg;
+        while (n_seg > 1 && lv.h - (n_seg - 1) * RL < 2 * lv.s_det + 4) n_seg--;  // the last segment takes what is left
+
         float* px = B.Lx + off;
         float* py = B.Ly + off;
         float* pd = B.Ldet + off;
+        static const bool rings_in_smem = getenv("AKZ_DET_SMEM") != nullptr;  // A/B switch: the shared-memory ring kernel
         auto go = [&](auto s_tag) {
             constexpr int S = decltype(s_tag)::value;
             const int sx = (lv.w + StreamGeo<S>::UX - 1) / StreamGeo<S>::UX;
-            k_detector_stream<S><<<dim3(sx * n_seg, 1, L.batch), 32, 0, L.stream>>>(ls, img_px, px, py, pd, mk, (size_t)P.dev.mask_words, p, sx, n_seg, RL);
+            if (rings_in_smem)
+                k_detector_stream<S><<<dim3(sx * n_seg, 1, L.batch), 32, 0, L.stream>>>(ls, img_px, px, py, pd, mk, (size_t)P.dev.mask_words, p, sx, n_seg, RL);
+            else
+                k_detector_tmem<S><<<dim3((sx * n_seg + DT_WARPS - 1) / DT_WARPS, 1, L.batch), DT_WARPS * 32, 0, L.stream>>>(ls, img_px, px, py, pd, mk, (size_t)P.dev.mask_words, p, sx, n_seg, RL);
         };
         if (lv.s_det == 2) go(std::integral_constant<int, 2>{});
         else if (lv.s_det == 3) go(std::integral_constant<int, 3>{});
