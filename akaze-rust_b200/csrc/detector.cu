@@ -555,10 +555,11 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
         const float v[4] = {Lc.x, Lc.y, Lc.z, Lc.w};
         float e[12];
         h_neighbours<S>(v, e);
+        {
+            const float el[4] = {e[4 - S], e[5 - S], e[6 - S], e[7 - S]}, er[4] = {e[4 + S], e[5 + S], e[6 + S], e[7 + S]};
+            tap3x4(n, wn, n, el, v, er, R.a);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            R.a[j] = (n * e[4 + j - S] + wn * e[4 + j]) + n * e[4 + j + S];
-            R.bo[j] = e[4 + j + S] - e[4 + j - S];
+            for (int j = 0; j < 4; j++) R.bo[j] = er[j] - el[j];
         }
         det_fix_cols<S, BORDER>(k, R.a);
         det_fix_cols<S, BORDER>(k, R.bo);
@@ -570,10 +571,10 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
         float4 a_m = rg.template load<0>(rm), b_m = rg.template load<1>(rm), b_0 = rg.template load<1>(s1);
         rg.fence3(a_m, b_m, b_0);
         R.lx[0] = R.a[0] - a_m.x; R.lx[1] = R.a[1] - a_m.y; R.lx[2] = R.a[2] - a_m.z; R.lx[3] = R.a[3] - a_m.w;
-        R.ly[0] = (n * b_m.x + wn * b_0.x) + n * R.bo[0];
-        R.ly[1] = (n * b_m.y + wn * b_0.y) + n * R.bo[1];
-        R.ly[2] = (n * b_m.z + wn * b_0.z) + n * R.bo[2];
-        R.ly[3] = (n * b_m.w + wn * b_0.w) + n * R.bo[3];
+        {
+            const float bm[4] = {b_m.x, b_m.y, b_m.z, b_m.w}, b0[4] = {b_0.x, b_0.y, b_0.z, b_0.w};
+            tap3x4(n, wn, n, bm, b0, R.bo, R.ly);
+        }
         if (STEADY) {
             if (k.xout && sp.st1) {
                 st4(sp.px, make_float4(R.lx[0], R.lx[1], R.lx[2], R.lx[3]));
@@ -592,10 +593,11 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
     if (row1) {
         float e[12];
         h_neighbours<S>(R.lx, e);
+        {
+            const float el[4] = {e[4 - S], e[5 - S], e[6 - S], e[7 - S]}, er[4] = {e[4 + S], e[5 + S], e[6 + S], e[7 + S]};
+            tap3x4(n, wn, n, el, R.lx, er, R.cc);
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            R.cc[j] = (n * e[4 + j - S] + wn * e[4 + j]) + n * e[4 + j + S];
-            R.ee[j] = e[4 + j + S] - e[4 + j - S];
+            for (int j = 0; j < 4; j++) R.ee[j] = er[j] - el[j];
         }
         h_neighbours<S>(R.ly, e);
 #pragma unroll
@@ -613,11 +615,14 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
         rg.fence5(c_m, e_m, e_0, d_m, d_0);
         const float cm[4] = {c_m.x, c_m.y, c_m.z, c_m.w}, em[4] = {e_m.x, e_m.y, e_m.z, e_m.w}, e0[4] = {e_0.x, e_0.y, e_0.z, e_0.w};
         const float dm[4] = {d_m.x, d_m.y, d_m.z, d_m.w}, d0[4] = {d_0.x, d_0.y, d_0.z, d_0.w};
+        float lyy4[4], lxy4[4];
+        tap3x4(n, wn, n, dm, d0, R.dd, lyy4);
+        tap3x4(n, wn, n, em, e0, R.ee, lxy4);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const float lxx = R.cc[j] - cm[j];
-            const float lyy = (n * dm[j] + wn * d0[j]) + n * R.dd[j];
-            const float lxy = (n * em[j] + wn * e0[j]) + n * R.ee[j];
+            const float lyy = lyy4[j];
+            const float lxy = lxy4[j];
             R.det_m[j] = R.det_0[j];
             R.det_0[j] = R.det_p[j];
             R.det_p[j] = ((lxx * lyy) - (lxy * lxy)) * k.quat;  // detector_response.rs:52

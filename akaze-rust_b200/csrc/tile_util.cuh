@@ -17,6 +17,33 @@ __device__ __forceinline__ float4 sub4(const float4& a, const float4& b) {
     return make_float4(a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w);
 }
 
+// Packed f32x2 multiply (FMUL2, new on sm_100): two IEEE products in one issue slot, each rounded exactly like a scalar
+// FMUL. Only the PRODUCTS of the 3-tap filters are packed; their sums stay scalar FADDs, because ptxas 12.9 contracts
+// mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false (profiles/r1z_pipes_microbench.txt), which would break
+// the bit-exact match with the reference's unfused arithmetic.
+__device__ __forceinline__ void mul2(float a0, float a1, float k, float& p0, float& p1) {
+    asm("{.reg .b64 ra, rk, rp;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rk, {%4, %4};\n\t"
+        "mul.rn.f32x2 rp, ra, rk;\n\t"
+        "mov.b64 {%0, %1}, rp;}"
+        : "=f"(p0), "=f"(p1)
+        : "f"(a0), "f"(a1), "f"(k));
+}
+// out[j] = (k0 * a[j] + k1 * b[j]) + k2 * c[j], j = 0..3, in tap order (products packed in pairs, sums scalar)
+__device__ __forceinline__ void tap3x4(float k0, float k1, float k2, const float (&a)[4], const float (&b)[4], const float (&c)[4],
+                                       float (&out)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; j += 2) {
+        float pa0, pa1, pb0, pb1, pc0, pc1;
+        mul2(a[j], a[j + 1], k0, pa0, pa1);
+        mul2(b[j], b[j + 1], k1, pb0, pb1);
+        mul2(c[j], c[j + 1], k2, pc0, pc1);
+        out[j] = (pa0 + pb0) + pc0;
+        out[j + 1] = (pa1 + pb1) + pc1;
+    }
+}
+
 // v[0..11] = row[cx-4 .. cx+7] (cx a multiple of 4)
 __device__ __forceinline__ void load12(const float* row, int cx, float (&v)[12]) {
     const float4 a = ld4(row + cx - 4), b = ld4(row + cx), c = ld4(row + cx + 4);
