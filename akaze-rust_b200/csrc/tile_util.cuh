@@ -30,6 +30,15 @@ __device__ __forceinline__ void mul2(float a0, float a1, float k, float& p0, flo
         : "=f"(p0), "=f"(p1)
         : "f"(a0), "f"(a1), "f"(k));
 }
+__device__ __forceinline__ void mul2v(float a0, float a1, float b0, float b1, float& p0, float& p1) {
+    asm("{.reg .b64 ra, rb, rp;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rp, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rp;}"
+        : "=f"(p0), "=f"(p1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 // out[j] = (k0 * a[j] + k1 * b[j]) + k2 * c[j], j = 0..3, in tap order (products packed in pairs, sums scalar)
 __device__ __forceinline__ void tap3x4(float k0, float k1, float k2, const float (&a)[4], const float (&b)[4], const float (&c)[4],
                                        float (&out)[4]) {
