@@ -268,13 +268,12 @@ std::string build_plan(uint32_t w, uint32_t h, const akz_config& cfg, Plan* P) {
 using namespace akz;
 
 // ---- context -----------------------------------------------------------------------------------
-// One extraction call is cut into sub-batches that flow through a two-stage software pipeline:
-//   stage A (stream `stream`):    upload-independent stencil work -- level 0, contrast, per level
-//                                 prep / FED / detector, candidate compaction;
-//   stage B (stream `stream_kp`): the latency-bound keypoint stages -- cache pass, filter/refine,
-//                                 orientation, descriptors.
-// Two "lanes" of work buffers alternate between consecutive sub-batches, so stage B of sub-batch i
-// overlaps stage A of sub-batch i+1. Results of all images of the call live in context-level arrays.
+// One extraction call is cut into sub-batches that flow through a software pipeline (run_pipeline):
+//   S(i) (stream `stream`):     stencil work -- level 0, contrast, per level prep / FED / detector, candidate compaction;
+//   D(i) (stream `stream_kp`):  the latency-bound cache pass, one warp per image, started after S(i) and F(i-1);
+//   F(i) (stream `stream`):     filter/refine, orientation, descriptors, enqueued after S(i+1).
+// Two "lanes" of work buffers alternate between consecutive sub-batches, so D(i) overlaps S(i+1) and nothing else does.
+// Results of all images of the call live in context-level arrays.
 struct Lane {
     Buffers buf;
     std::vector<void*> allocs;

@@ -476,6 +476,7 @@ struct RingSmem {
     __device__ __forceinline__ float4 load(int h) const { return ring[A][h][lane]; }
     template <int A>
     __device__ __forceinline__ void store(int h, const float4& v) const { ring[A][h][lane] = v; }
+    __device__ __forceinline__ int uniform(int h) const { return h; }
     __device__ __forceinline__ void row_begin() const {}
     __device__ __forceinline__ void fence3(float4&, float4&, float4&) const {}
     __device__ __forceinline__ void fence5(float4&, float4&, float4&, float4&, float4&) const {}
@@ -489,29 +490,35 @@ struct RingTmem {
     unsigned int base;                // TMEM address: this warp's first lane, first column of the CTA's allocation
     float4 (*ring_a)[32];             // S = 4 only: ring A of this warp in shared memory
     int lane;
-    // a ring row is named by a handle = 4 * slot (its column offset inside one array); the array's columns and the warp's
-    // TMEM base are compile-time / loop-invariant, so a steady row spends two adds on addressing instead of one per access
-    __device__ __forceinline__ int handle(int slot) const { return 4 * slot; }
-    __device__ __forceinline__ int next(int h) const { return (h + 4 == 4 * D) ? 0 : h + 4; }
-    template <int A>
-    __device__ __forceinline__ unsigned int addr(int h) const {
-        return base + (unsigned int)((A_IN_SMEM ? A - 1 : A) * D * 4) + (unsigned int)h;
-    }
+    // a ring row is named by a handle = the TMEM address of its four columns in array 0; the other arrays sit at
+    // compile-time column offsets that go into the instruction's immediate field (tmem[UR + imm]), so a steady row moves
+    // two handles to uniform registers instead of one address per access
+    __device__ __forceinline__ int handle(int slot) const { return (int)(base + 4u * (unsigned int)slot); }
+    __device__ __forceinline__ int next(int h) const { return (h + 4 == (int)(base + 4u * D)) ? (int)base : h + 4; }
     template <int A>
     __device__ __forceinline__ float4 load(int h) const {
-        if (A_IN_SMEM && A == 0) return ring_a[h >> 2][lane];
+        if (A_IN_SMEM && A == 0) return ring_a[(h - (int)base) >> 2][lane];
         unsigned int r0, r1, r2, r3;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(addr<A>(h)) : "memory");
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4 + %5];"
+                     : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                     : "r"(h), "n"((A_IN_SMEM ? A - 1 : A) * D * 4)
+                     : "memory");
         return make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3));
     }
     template <int A>
     __device__ __forceinline__ void store(int h, const float4& v) const {
         if (A_IN_SMEM && A == 0) {
-            ring_a[h >> 2][lane] = v;
+            ring_a[(h - (int)base) >> 2][lane] = v;
             return;
         }
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr<A>(h)), "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w)) : "memory");
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0 + %1], {%2, %3, %4, %5};" ::"r"(h), "n"((A_IN_SMEM ? A - 1 : A) * D * 4),
+                     "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w))
+                     : "memory");
     }
+    // LDTM/STTM take their address from a UNIFORM register; a handle kept in an ordinary register costs one R2UR per access
+    // (23 per row). A warp-wide max of the (already warp-uniform) handle is a single CREDUX that lands in a uniform
+    // register, which all accesses of the row then share.
+    __device__ __forceinline__ int uniform(int h) const { return (int)__reduce_max_sync(0xffffffffu, (unsigned int)h); }
     // a row's stores are read again S rows later at the earliest: one wait per row covers them
     __device__ __forceinline__ void row_begin() const { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
     // the loaded registers are in/out operands of the wait, so that no use of them can be scheduled above it
@@ -547,8 +554,8 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
     const float n = k.n, wn = k.wn;
     const int lane = k.lane;
     // ring slots of rows c, c-S, c-2S, c-3S
-    const int s0 = STEADY ? sl[0] : rg.handle(c % D);
-    const int s1 = STEADY ? sl[1] : rg.handle((c - S) % D);
+    const int s0 = rg.uniform(STEADY ? sl[0] : rg.handle(c % D));
+    const int s1 = rg.uniform(STEADY ? sl[1] : rg.handle((c - S) % D));
     const int o1 = c - S, o2 = c - 2 * S, o3 = o2 - 1;
     // ---- A = H_main(Lsmooth), Bo = H_off(Lsmooth), row c (rows beyond yhi keep the registers of row yhi)
     if (STEADY || c <= k.yhi) {
@@ -567,7 +574,7 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
     // ---- Lx = V_off(A), Ly = V_main(Bo), row o1 = c - S
     const bool row1 = STEADY || (o1 >= k.ylo && o1 <= k.yhi);
     if (row1) {
-        const int rm = STEADY ? sl[0] : rg.handle(max(o1 - S, k.ylo) % D);  // row c - 2S shares the slot of row c
+        const int rm = STEADY ? s0 : rg.uniform(rg.handle(max(o1 - S, k.ylo) % D));  // row c - 2S shares the slot of row c
         float4 a_m = rg.template load<0>(rm), b_m = rg.template load<1>(rm), b_0 = rg.template load<1>(s1);
         rg.fence3(a_m, b_m, b_0);
         R.lx[0] = R.a[0] - a_m.x; R.lx[1] = R.a[1] - a_m.y; R.lx[2] = R.a[2] - a_m.z; R.lx[3] = R.a[3] - a_m.w;
@@ -608,8 +615,8 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
     }
     // ---- Lxx = V_off(C), Lxy = V_main(E), Lyy = V_main(D), Ldet, row o2 = c - 2S
     if (STEADY || (o2 >= k.ylo && o2 <= k.yhi)) {
-        const int rm = STEADY ? sl[1] : rg.handle(max(o2 - S, k.ylo) % D);  // row c - 3S shares the slot of row c - S
-        const int r0 = STEADY ? sl[0] : rg.handle((o2 + 2 * D) % D);
+        const int rm = STEADY ? s1 : rg.uniform(rg.handle(max(o2 - S, k.ylo) % D));  // row c - 3S shares the slot of row c - S
+        const int r0 = STEADY ? s0 : rg.uniform(rg.handle((o2 + 2 * D) % D));
         float4 c_m = rg.template load<2>(rm), e_m = rg.template load<3>(rm), e_0 = rg.template load<3>(r0);
         float4 d_m = rg.template load<4>(rm), d_0 = rg.template load<4>(r0);
         rg.fence5(c_m, e_m, e_0, d_m, d_0);
