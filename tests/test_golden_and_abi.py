@@ -99,3 +99,61 @@ def test_ransac_host(akz):
     out = ransac.remove_outliers(kp0, kp1, m, 20, 0.05, 3.0)
     assert out.dtype == akz.MATCH_DTYPE and len(out) <= n
     assert set(out["index_0"]).issubset(set(m["index_0"]))
+
+
+def test_no_contracted_packed_fma_in_the_library(akz):
+    """The stencils use packed f32x2 multiplies (FMUL2) but must never contain a packed fused multiply-add: ptxas
+    contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 even under --fmad=false, which would silently break the bit-exact
+    match with the reference's unfused arithmetic (profiles/r1z_pipes_microbench.txt). Scalar FFMA may only appear in
+    the correctly rounded division / sqrt / double-precision helper sequences the compiler emits, never in the filters:
+    the streaming kernels' steady loops are checked to be free of it."""
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not installed")
+    sass = subprocess.run(["cuobjdump", "-sass", akz.LIB_PATH], capture_output=True, text=True).stdout
+    assert "FMUL2" in sass, "the packed-product path is gone (or the library was built for another arch)"
+    assert "FFMA2" not in sass, "ptxas contracted a packed multiply-add: results would no longer be bit-exact"
+    # per kernel: the detector, FED and smooth+gradient stream kernels contain no scalar FFMA at all
+    for fn in re.split(r"\n\s*Function : ", sass)[1:]:
+        name = fn.split("\n", 1)[0]
+        if any(k in name for k in ("k_detector_tmem", "k_detector_stream", "k_fed_pp")):
+            assert " FFMA " not in fn, name
+
+
+def test_contrast_bin_is_a_monotone_step_function():
+    """k_contrast_hist_ew replaces the per-pixel f64 sqrt / divide / floor of contrast_factor.rs:45-50 by a lookup in a
+    table of thresholds found by bisection (k_contrast_thresholds). That is exact iff bin(g2) is non-decreasing in g2
+    and the bisection evaluates the same formula; restated in numpy float64 (IEEE, like the device code) and checked
+    on random gradients, including values next to every threshold."""
+    def bin_of(g2, hmax, n_bins):
+        modg = np.sqrt(g2)
+        bf = np.floor(n_bins * (modg / hmax))
+        return np.minimum(np.where(bf > 0.0, np.minimum(bf, n_bins), 0.0), n_bins - 1).astype(np.int64)
+
+    rng = np.random.default_rng(7)
+    n_bins = 300
+    lx = rng.normal(0, 0.02, 200000).astype(np.float32).astype(np.float64)
+    ly = rng.normal(0, 0.02, 200000).astype(np.float32).astype(np.float64)
+    g2 = lx * lx + ly * ly
+    g2 = g2[g2 > 0]
+    hmax = float(np.sqrt(g2.max()))
+    # thresholds by bisection over the f64 bit patterns (positive doubles order like u64)
+    thr = np.empty(n_bins + 1)
+    thr[0], thr[n_bins] = 0.0, np.inf
+    for b in range(1, n_bins):
+        lo, hi = np.uint64(1), np.uint64(0x7FEFFFFFFFFFFFFF)
+        while hi - lo > 1:
+            mid = lo + ((hi - lo) >> np.uint64(1))
+            if bin_of(np.array([mid], np.uint64).view(np.float64), hmax, n_bins)[0] >= b:
+                hi = mid
+            else:
+                lo = mid
+        thr[b] = np.array([hi], np.uint64).view(np.float64)[0]
+    assert np.all(np.diff(thr[:-1]) >= 0)
+    by_table = np.searchsorted(thr, g2, side="right") - 1
+    assert np.array_equal(by_table, bin_of(g2, hmax, n_bins))
+    # the doubles on either side of every threshold
+    edge = np.concatenate([np.nextafter(thr[1:-1], 0.0), thr[1:-1], np.nextafter(thr[1:-1], np.inf)])
+    edge = edge[edge > 0]
+    assert np.array_equal(np.searchsorted(thr, edge, side="right") - 1, bin_of(edge, hmax, n_bins))
