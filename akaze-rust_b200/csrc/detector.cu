@@ -372,10 +372,11 @@ k_detector_fast(const float* __restrict__ lsmooth, size_t img_px, float* __restr
 //   C, E, D (row c-S)        <- H taps of that Lx / Ly row
 //   Lxx, Lxy, Lyy, Ldet (row c-2S) <- V taps of C / E / D rows c-3S, c-2S, c-S
 //   candidates (row c-2S-1)  <- Ldet rows c-2S-2 .. c-2S kept in registers
-// The rows a V tap needs again later live in per-lane ring buffers in shared memory (each lane reads
-// back only what it wrote itself: no barriers at all); nothing is recomputed vertically inside a
-// segment, and the shared-memory traffic is 13 128-bit accesses per 4 pixels instead of ~45 in the
-// tile kernel, which ncu shows to be shared-memory bound (profiles/r1f). fill_border: every pass of
+// The rows a V tap needs again later live in per-lane ring buffers (each lane reads back only what it
+// wrote itself: no barriers in the row loop) -- in TENSOR MEMORY in the default kernel (k_detector_tmem,
+// RingTmem below), in shared memory in k_detector_stream (RingSmem); nothing is recomputed vertically
+// inside a segment, and the ring traffic is 13 128-bit accesses per 4 pixels instead of ~45 shared-memory
+// accesses in the tile kernel, which ncu shows to be shared-memory bound (profiles/r1f). fill_border: every pass of
 // the reference clamps with the same half-width S, so rows < S / > H-1-S of every intermediate equal
 // rows S / H-1-S: ring reads clamp their row index, rows beyond H-1-S reuse the registers of row
 // H-1-S, and border rows are written when the row they replicate is produced. Columns: the H-pass
@@ -404,8 +405,8 @@ __device__ __forceinline__ void h_neighbours(const float (&v)[4], float (&ext)[1
 }
 
 // Row c of the pipeline. STEADY: every stage is active, no ring read clamps, no border rows to replicate,
-// all output rows inside the segment (the caller guarantees it) -> no row tests at all, and the ring slots of
-// rows c, c-S, c-2S, c-3S come in as sl[0..3] (advanced by the caller) instead of being derived from c.
+// -> no row tests besides the three warp-uniform flags of DetSteadyPtrs (stores / candidate test on or off), and the ring
+// handles of rows c and c-S (which rows c-2S and c-3S share) come in as sl[0..1], advanced by the caller.
 // BORDER: the strip touches the first/last S columns of the image. The steady loop is deliberately NOT
 // unrolled: an 8x unrolled body (35 KB of SASS per variant) ran 55 % slower on instruction-fetch stalls
 // (profiles/r1i: stall_no_inst 29 % of samples).
