@@ -41,3 +41,45 @@ def test_keypoint_stages_match_independent_restatement(oracle, akz, which):
         kp["angle"] = ang
         d = K.mldb_descriptor(kp, lt, lx, ly)
         assert np.array_equal(d, ref.descriptors[i]), i
+
+
+def _descriptor_match_literal(d0, d1, distance_threshold, lowes_ratio):
+    """feature_matching.rs:23-123 taken literally, bail-out included (it may return a PARTIAL distance that is larger
+    than the running second minimum; the update rule then ignores it, which is why the GPU may use full distances)."""
+    pop = np.array([bin(i).count("1") for i in range(256)])
+    out = []
+    for i, a in enumerate(d0):
+        mn, mj, sec = distance_threshold, 0, distance_threshold
+        for j, b in enumerate(d1):
+            dist = 0
+            for x0, x1 in zip(a, b):
+                dist += pop[x0 ^ x1]
+                if dist > sec:
+                    break
+            if dist < mn:
+                sec, mn, mj = mn, dist, j
+            elif dist < sec:
+                sec = dist
+        if float(mn) < float(sec) * lowes_ratio ** 2 and mn < distance_threshold:
+            out.append((i, mj, float(mn)))
+    return out
+
+
+def test_descriptor_match_matches_independent_restatement(oracle):
+    import os
+    g = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    a = np.load(os.path.join(g, "features_1.npz"))["descriptors"][:60]
+    b = np.load(os.path.join(g, "features_2.npz"))["descriptors"][:400]
+    rng = np.random.default_rng(3)
+    b = b.copy()
+    b[rng.integers(0, len(b), 25)] = a[rng.integers(0, len(a), 25)]  # exact and near duplicates: ties on the minimum
+    b[7] = b[3]
+    for lowes in (0.86, 1.5):
+        m = oracle.descriptor_match(a, b, 10000, lowes)
+        lit = _descriptor_match_literal(a.tolist(), b.tolist(), 10000, lowes)
+        assert [(int(r["index_0"]), int(r["index_1"]), float(r["distance"])) for r in m] == lit
+    # raw top-2 against a vectorised numpy brute force (lowest index wins ties)
+    d = np.unpackbits(a[:, None, :] ^ b[None, :, :], axis=2).sum(axis=2)
+    bi, best, second = oracle.match_top2(a, b)
+    assert np.array_equal(bi, d.argmin(axis=1)) and np.array_equal(best, d.min(axis=1))
+    assert np.array_equal(second, np.sort(d, axis=1)[:, 1])
