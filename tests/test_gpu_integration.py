@@ -37,3 +37,18 @@ def test_match_features(akz):
     assert 550 <= len(putative) <= 565          # oracle: 557
     assert 0 < len(matches) <= len(putative)
     assert set(zip(matches["index_0"], matches["index_1"])).issubset(set(zip(putative["index_0"], putative["index_1"])))
+
+
+def test_command_line_tools(akz, tmp_path):
+    # akaze-util/src/bin/extract_and_match.rs + match_features.rs on the engine (akaze-rust_b200/cli.py)
+    from akaze_rust_b200 import cli, formats
+    prefix = str(tmp_path / "run")
+    assert cli.main(["extract_and_match", os.path.join(TEST_DATA, "1.jpg"), os.path.join(TEST_DATA, "2.jpg"), prefix]) == 0
+    k0, d0 = formats.deserialize_features_from_file(prefix + "-extractions_0.cbor")
+    k1, d1 = formats.deserialize_features_from_file(prefix + "-extractions_1.cbor")
+    assert (len(k0), len(k1)) == (7395, 5629) and len(d0[0]) == 61
+    m = formats.deserialize_matches_from_file(prefix + "-matches.cbor")
+    assert 0 < len(m) <= 565
+    out = str(tmp_path / "m.json")
+    assert cli.main(["match_features", prefix + "-extractions_0.cbor", prefix + "-extractions_1.cbor", out]) == 0
+    assert 0 < len(formats.deserialize_matches_from_file(out)) <= 565
