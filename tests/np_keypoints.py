@@ -192,3 +192,59 @@ def mldb_descriptor(kp, lt, lx, ly, channels=3, pattern=10):
                         out[dpos >> 3] |= np.uint8(1 << (dpos & 7))
                     dpos += 1
     return out
+
+
+def find_scale_space_extrema_vec(ldets, levels, detector_threshold=0.001, derivative_factor=1.5):
+    """Same semantics as find_scale_space_extrema, with the linear cache scan of every candidate done by numpy (first
+    matching slot via argmax over the whole cache), so that the reference's full-size test images are affordable."""
+    cap = 1 << 16
+    cx, cy, cr, cs = (np.zeros(cap, F) for _ in range(4))
+    cc = np.full(cap, -10, np.int64)
+    co = np.zeros(cap, np.int64)
+    n = 0
+    smax = F(10.0) * F(np.sqrt(F(2.0)))
+    thr = F(detector_threshold)
+    for e_id, (ldet, lv) in enumerate(zip(ldets, levels)):
+        h, w = ldet.shape
+        buf = ldet.reshape(-1)
+        size = F(lv["esigma"] * derivative_factor)
+        ratio = powf(2.0, F(lv["octave"]))
+        sigma_size = roundf(size / ratio)
+        idx = np.arange(w + 1, buf.size - w - 1)
+        v = buf[idx]
+        cand = (idx % w != 0) & (v > thr) & (v > buf[idx + 1]) & (v > buf[idx - 1]) & (v > buf[idx - w]) & (v > buf[idx + w])
+        s2 = size * size
+        for i in idx[cand]:
+            x, y = int(i % w), int(i // w)
+            resp = F(abs(buf[i]))
+            px, py = F(x), F(y)
+            qx, qy = px * ratio, py * ratio
+            id_repeated, is_repeated, is_extremum = 0, False, True
+            if n:
+                cls = cc[:n]
+                dx = qx - cx[:n]
+                dy = qy - cy[:n]
+                hit = ((cls == e_id) | (cls == e_id - 1)) & (dx * dx + dy * dy <= s2)
+                if hit.any():
+                    k = int(np.argmax(hit))  # the FIRST slot that matches decides (:60-84)
+                    if resp > cr[k]:
+                        id_repeated, is_repeated = k, True
+                    else:
+                        is_extremum = False
+            if not is_extremum:
+                continue
+            if (roundf(px - smax * sigma_size) - F(1) < 0 or roundf(px + smax * sigma_size) + F(1) >= F(w)
+                    or roundf(py - smax * sigma_size) - F(1) < 0 or roundf(py + smax * sigma_size) + F(1) >= F(h)):
+                continue
+            k = id_repeated if is_repeated else n
+            cx[k], cy[k] = qx + F(0.5) * (ratio - F(1.0)), qy + F(0.5) * (ratio - F(1.0))
+            cr[k], cs[k], cc[k], co[k] = resp, size, e_id, int(lv["octave"])
+            if not is_repeated:
+                n += 1
+    out = []
+    for i in range(n):
+        later = slice(i, n)
+        dx, dy = cx[i] - cx[later], cy[i] - cy[later]
+        if not ((cc[later] == cc[i] + 1) & (dx * dx + dy * dy <= cs[i] * cs[i])).any():
+            out.append(dict(x=cx[i], y=cy[i], response=cr[i], size=cs[i], octave=int(co[i]), class_id=int(cc[i])))
+    return out, n

@@ -83,3 +83,34 @@ def test_descriptor_match_matches_independent_restatement(oracle):
     bi, best, second = oracle.match_top2(a, b)
     assert np.array_equal(bi, d.argmin(axis=1)) and np.array_equal(best, d.min(axis=1))
     assert np.array_equal(second, np.sort(d, axis=1)[:, 1])
+
+
+@pytest.mark.parametrize("name", ["1", "2"])
+def test_reference_test_images_full_size(oracle, akz, name):
+    """The reference's own test-data/1.jpg and 2.jpg at full size: the independent restatement reproduces the committed
+    golden keypoints (all 7 395 / 5 629, every field) from the oracle's Ldet images -- including the cases where the
+    upper-scale filter and the sub-pixel test drop cache entries -- and angles + descriptors of a sample."""
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    gray = akz.load_gray(os.path.join(gold, name + ".jpg"))
+    ref = oracle.extract(oracle.unit_float_from_u8(gray), threads=4)
+    g = np.load(os.path.join(gold, "features_%s.npz" % name))
+    ldets = [ref.image(l, "Ldet") for l in range(ref.num_levels)]
+    cache_out, n_cache = K.find_scale_space_extrema_vec(ldets, ref.levels)
+    assert n_cache == ref.num_cache
+    kps = K.do_subpixel_refinement(cache_out, ldets)
+    gk = g["keypoints"]
+    assert len(kps) == len(gk) and len(kps) <= n_cache  # 2.jpg: 5 630 cache entries, 5 629 survive the upper-scale filter
+    for f in ("x", "y", "response", "size"):
+        assert np.array_equal(np.array([k[f] for k in kps], np.float32), gk[f]), f
+    assert np.array_equal(np.array([k["class_id"] for k in kps]), gk["class_id"])
+    planes = {}
+    for i in range(0, len(kps), 97):
+        kp = kps[i]
+        lv = kp["class_id"]
+        if lv not in planes:
+            planes[lv] = (ref.image(lv, "Lx"), ref.image(lv, "Ly"), ref.image(lv, "Lt"))
+        lx, ly, lt = planes[lv]
+        kp["angle"] = K.compute_main_orientation(kp, lx, ly, kp["octave"])
+        assert kp["angle"] == gk["angle"][i], i
+        assert np.array_equal(K.mldb_descriptor(kp, lt, lx, ly), g["descriptors"][i]), i
