@@ -84,7 +84,26 @@ EXPORTS = [
     "akz_features_contrast_factor", "akz_features_num_candidates", "akz_features_num_cache",
     "akz_features_evolution_download", "akz_features_free", "akz_match_top2", "akz_match_top2_device",
     "akz_merge_top2_device", "akz_descriptor_match",
+    "akz_comm_unique_id", "akz_context_comm_init", "akz_context_comm_init_all", "akz_context_comm_destroy",
+    "akz_match_top2_sharded_device", "akz_match_top2_sharded",
 ]
+
+
+def _nccl_hint():
+    """The multi-GPU matcher binds NCCL at run time (dlopen "libnccl.so.2"); point it at the wheel's copy when the
+    process has not loaded one already (torch loads its own) and the caller did not choose."""
+    if os.environ.get("AKZ_NCCL_LIB"):
+        return
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (list(spec.submodule_search_locations) if spec and spec.submodule_search_locations else []):
+            cand = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                os.environ["AKZ_NCCL_LIB"] = cand
+                return
+    except Exception:  # noqa: BLE001 -- a hint only; akz_comm_* reports a missing NCCL itself
+        pass
 
 
 def lib():
@@ -92,6 +111,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
+    _nccl_hint()
     if not os.path.exists(LIB_PATH):
         raise ImportError("libakaze_b200.so is missing: run `python __graft_entry__.py` (nvcc, sm_100a) first; "
                           "there is no CPU fallback")
@@ -145,6 +165,12 @@ def lib():
     L.akz_merge_top2_device.argtypes = [vp, vp, C.c_uint32, C.c_uint64, vp]
     L.akz_descriptor_match.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint32, C.c_size_t, C.c_uint64,
                                        C.c_double, vp, C.POINTER(C.c_uint64)]
+    L.akz_comm_unique_id.argtypes = [vp]
+    L.akz_context_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.akz_context_comm_init_all.argtypes = [C.POINTER(vp), C.c_int]
+    L.akz_context_comm_destroy.argtypes = [vp]
+    L.akz_match_top2_sharded_device.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint32, vp]
+    L.akz_match_top2_sharded.argtypes = [C.POINTER(vp), C.c_int, vp, C.c_uint64, vp, C.c_uint64, C.c_uint32, C.c_size_t, vp]
     _lib = L
     return L
 
@@ -182,9 +208,10 @@ class EvolutionStep:
 class Features:
     """Owns one akz_features handle: keypoints, descriptors and (optionally) the evolutions."""
 
-    def __init__(self, handle):
+    def __init__(self, handle, engine=None):
         L = lib()
         self._h = handle
+        self._engine = engine  # keeps the engine alive while its evolutions can still be downloaded
         self.count = int(L.akz_features_count(handle))
         self.descriptor_len = L.akz_features_descriptor_len(handle)
         self.contrast_factor = L.akz_features_contrast_factor(handle)
@@ -236,8 +263,16 @@ class Features:
         return self._evo
 
     def evolution(self, level, kind):
+        """One image of EvolutionStep `level`. Level 0 has no Lflow/Lstep: they stay 0x0 as in the reference
+        (evolution.rs:118-119 allocates them empty, lib.rs:78 starts the diffusion loop at level 1)."""
         k = IMAGE_KINDS[kind] if isinstance(kind, str) else int(kind)
+        if not self._h:
+            raise AkazeError(1, "features were closed: evolution images are downloaded from the device on demand")
+        if self._engine is not None and not self._engine._h:
+            raise AkazeError(1, "the engine of these features was closed")
         ev = self.evolutions[level]
+        if level == 0 and k in (IMAGE_KINDS["Lflow"], IMAGE_KINDS["Lstep"]):
+            return np.zeros((0, 0), np.float32)
         out = np.empty((ev.height, ev.width), np.float32)
         _check(lib().akz_features_evolution_download(self._h, level, k, out.ctypes.data))
         return out
@@ -266,7 +301,16 @@ def _pad64(d):
     d = np.ascontiguousarray(d, np.uint8)
     if d.ndim != 2:
         raise ValueError("descriptors must be a 2-D uint8 array")
+    if d.shape[1] > DESCRIPTOR_STRIDE:
+        raise ValueError("descriptor rows are at most %d bytes, got %d" % (DESCRIPTOR_STRIDE, d.shape[1]))
     return d
+
+
+def _gray2d(gray, dtype):
+    g = np.ascontiguousarray(gray, dtype)
+    if g.ndim != 2:
+        raise ValueError("expected a 2-D gray image, got shape %r (convert with to_luma_u8 first)" % (g.shape,))
+    return g
 
 
 class Engine:
@@ -330,23 +374,25 @@ class Engine:
 
     # -- extraction
     def extract_u8(self, gray, config=None):
-        gray = np.ascontiguousarray(gray, np.uint8)
+        gray = _gray2d(gray, np.uint8)
         cfg = config or Config.default()
         out = C.c_void_p()
         _check(lib().akz_extract_u8(self._h, gray.ctypes.data, gray.shape[1], gray.shape[0], gray.strides[0],
                                     C.byref(cfg), C.byref(out)))
-        return Features(out)
+        return Features(out, self)
 
     def extract_f32(self, unit_gray, config=None):
-        img = np.ascontiguousarray(unit_gray, np.float32)
+        img = _gray2d(unit_gray, np.float32)
         cfg = config or Config.default()
         out = C.c_void_p()
         _check(lib().akz_extract_f32(self._h, img.ctypes.data, img.shape[1], img.shape[0], C.byref(cfg), C.byref(out)))
-        return Features(out)
+        return Features(out, self)
 
     def extract_batch_u8(self, grays, config=None):
-        grays = [np.ascontiguousarray(g, np.uint8) for g in grays]
+        grays = [_gray2d(g, np.uint8) for g in grays]
         n = len(grays)
+        if n == 0:
+            return []
         h, w = grays[0].shape
         if any(g.shape != (h, w) for g in grays):
             raise ValueError("all images of a batch must have the same size")
@@ -354,7 +400,7 @@ class Engine:
         ptrs = (C.c_void_p * n)(*[g.ctypes.data for g in grays])
         outs = (C.c_void_p * n)()
         _check(lib().akz_extract_batch_u8(self._h, n, ptrs, w, h, w, C.byref(cfg), outs))
-        return [Features(C.c_void_p(o)) for o in outs]
+        return [Features(C.c_void_p(o), self) for o in outs]
 
     def extract_batch_u8_device(self, d_ptr, n, width, height, stride=None, config=None):
         """Images already in device memory (n*height*stride bytes); returns per-image keypoint counts."""
@@ -393,12 +439,57 @@ class Engine:
         """ops::feature_matching::descriptor_match (feature_matching.rs:23-94)."""
         d0, d1 = _pad64(d0), _pad64(d1)
         stride = d0.shape[1]
+        if d1.shape[0] and d1.shape[1] != stride:
+            raise ValueError("both descriptor sets must have the same row length (%d vs %d)" % (stride, d1.shape[1]))
         desc_len = desc_len or min(stride, DESCRIPTOR_STRIDE)
         out = np.zeros(max(d0.shape[0], 1), MATCH_DTYPE)
         n = C.c_uint64()
         _check(lib().akz_descriptor_match(self._h, d0.ctypes.data, d0.shape[0], d1.ctypes.data, d1.shape[0], desc_len,
                                           stride, distance_threshold, lowes_ratio, out.ctypes.data, C.byref(n)))
         return out[:n.value].copy()
+
+    # -- multi-GPU matching: database sharded by index over the ranks, NCCL all-gather + merge inside the library
+    def comm_init(self, unique_id, rank, n_ranks):
+        """Joins a communicator of n_ranks engines (one process per GPU); unique_id from comm_unique_id() of rank 0."""
+        buf = (C.c_uint8 * COMM_UNIQUE_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        _check(lib().akz_context_comm_init(self._h, buf, int(rank), int(n_ranks)))
+
+    def comm_destroy(self):
+        _check(lib().akz_context_comm_destroy(self._h))
+
+    def match_top2_sharded_device(self, d_q, nq, d_db_shard, ndb_shard, db_index_base, d_out):
+        _check(lib().akz_match_top2_sharded_device(self._h, C.c_void_p(d_q), nq, C.c_void_p(d_db_shard), ndb_shard,
+                                                   db_index_base, C.c_void_p(d_out)))
+
+
+COMM_UNIQUE_ID_BYTES = 128
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the library (akz_comm_unique_id): 128 bytes to ship to the other ranks."""
+    buf = (C.c_uint8 * COMM_UNIQUE_ID_BYTES)()
+    _check(lib().akz_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def comm_init_all(engines):
+    """One process driving several GPUs: a communicator over `engines` (one per device), engines[i] = rank i."""
+    arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    _check(lib().akz_context_comm_init_all(arr, len(engines)))
+
+
+def match_top2_sharded(engines, q, db, desc_len=None):
+    """akz_match_top2_sharded: host buffers, the database sharded over the engines of one communicator."""
+    q, db = _pad64(q), _pad64(db)
+    stride = q.shape[1]
+    if db.shape[0] and db.shape[1] != stride:
+        raise ValueError("query and database descriptors must have the same row length")
+    desc_len = desc_len or min(stride, DESCRIPTOR_STRIDE)
+    out = np.zeros(q.shape[0], TOP2_DTYPE)
+    arr = (C.c_void_p * len(engines))(*[e._h for e in engines])
+    _check(lib().akz_match_top2_sharded(arr, len(engines), q.ctypes.data, q.shape[0], db.ctypes.data, db.shape[0], desc_len,
+                                        stride, out.ctypes.data))
+    return out
 
 
 # ---- module-level mirror of the crate's two public functions ----------------------------------------
@@ -430,6 +521,14 @@ def load_gray(path):
     """image::open + to_luma (lib.rs:171, image.rs:128) on the host."""
     from PIL import Image
     with Image.open(path) as im:
+        if im.mode in ("L", "1", "P", "I;16", "I", "F", "LA"):
+            # gray sources: the `image` crate's to_luma is the identity on Luma8 (no weights, no truncation)
+            if im.mode == "L":
+                return np.asarray(im).copy()
+            if im.mode == "LA":
+                return np.asarray(im)[..., 0].copy()
+            if im.mode != "P":
+                return np.asarray(im.convert("L")).copy()
         return to_luma_u8(np.asarray(im.convert("RGB")))
 
 

@@ -2,21 +2,26 @@
 
 --fmad=false: the reference (rustc) never contracts a*b+c into an FMA, and the parity target for the
 stencil stages is bit-exactness, so nvcc must not contract either.
+
+Every source is compiled to its own object file (in parallel, only when stale) and the objects are linked
+into one shared library; no relocatable device code is needed (no cross-file device calls).
 """
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libakaze_b200.so")
 SOURCES = ["akaze_api.cu", "scale_space.cu", "detector.cu", "keypoints.cu", "matcher.cu", "matcher_tc.cu"]
-HEADERS = ["common.cuh", os.path.join("..", "..", "include", "akaze_b200.h")]
+HEADERS = ["common.cuh", "tile_util.cuh", "nccl_dyn.h", os.path.join("..", "..", "include", "akaze_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "--fmad=false", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
 ]
 
 
@@ -27,27 +32,48 @@ def nvcc_path():
     return p
 
 
-def is_stale():
-    if not os.path.exists(LIB):
+def _deps(src):
+    return [os.path.join(CSRC, src)] + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
+
+
+def _obj(src):
+    return os.path.join(OBJ, src.replace(".cu", ".o"))
+
+
+def _stale(target, deps):
+    if not os.path.exists(target):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    t = os.path.getmtime(target)
     return any(os.path.getmtime(d) > t for d in deps)
+
+
+def is_stale():
+    return _stale(LIB, [d for s in SOURCES for d in _deps(s)])
 
 
 def build(force=False, verbose=False):
     """Compile every CUDA source for sm_100a into one shared library. Returns its path."""
     if not force and not is_stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    os.makedirs(OBJ, exist_ok=True)
+    nvcc = nvcc_path()
+
+    def compile_one(src):
+        if not force and not _stale(_obj(src), _deps(src)):
+            return ""
+        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", _obj(src)]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s%s" % (src, r.stdout, r.stderr))
+        return r.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
+        logs = list(ex.map(compile_one, SOURCES))
     if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-    r = subprocess.run(cmd, capture_output=True, text=True)
+        print("\n".join(logs))
+    r = subprocess.run([nvcc, "-shared", "-o", LIB] + [_obj(s) for s in SOURCES] + ["-ldl"], capture_output=True, text=True)
     if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
     return LIB
 
 

@@ -64,8 +64,8 @@ def cmd_extract_features(args, A=None):
         os.makedirs(args.debug_path, exist_ok=True)
         for i, e in enumerate(evolutions):
             for name in ("Lt", "Lsmooth", "Lx", "Ly", "Lflow", "Ldet"):
-                img = getattr(e, name, None)
-                if img is not None:
+                img = getattr(e, name, None)  # level 0 has 0x0 Lflow, like the reference: nothing to write
+                if img is not None and np.size(img):
                     np.save(os.path.join(args.debug_path, "%s_%02d.npy" % (name, i)), np.asarray(img, np.float32))
         log.info("Wrote the scale space as .npy files to %s (the PNG dumps of the reference are out of scope).", args.debug_path)
     return 0
@@ -74,8 +74,9 @@ def cmd_extract_features(args, A=None):
 def _match(A, f0, f1):
     k0, d0 = f0
     k1, d1 = f1
-    d0 = np.stack(d0) if len(d0) else np.zeros((0, 61), np.uint8)
-    d1 = np.stack(d1) if len(d1) else np.zeros((0, 61), np.uint8)
+    width = len(d0[0]) if len(d0) else (len(d1[0]) if len(d1) else 61)
+    d0 = np.stack(d0) if len(d0) else np.zeros((0, width), np.uint8)
+    d1 = np.stack(d1) if len(d1) else np.zeros((0, width), np.uint8)
     return A.match_features(k0, d0, k1, d1, 0.86, 1000, 3.0)
 
 

@@ -14,10 +14,13 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <memory>
 #include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
+#include "nccl_dyn.h"
 
 namespace akz {
 
@@ -322,7 +325,10 @@ struct Results {
 struct akz_context {
     int device = 0;
     uint32_t max_w = 0, max_h = 0, max_batch = 0, flags = 0;
+    std::recursive_mutex mu;           // every entry point that touches the context holds it: thread-safe per context
+    uint64_t id = 0;                   // unique per akz_create (handles check it: an address can be reused)
     uint32_t cand_cap = 262144, kp_cap = 65536;
+    bool caps_auto = true;             // capacities follow the image size until akz_context_set_limits is called
     uint32_t sub_batch = 128;          // images per pipeline sub-batch
     bool sub_batch_auto = true;        // chosen from the free device memory when the plan changes (see prepare)
     cudaStream_t stream = nullptr;     // stage A, copies, and the stream callers may time on
@@ -359,12 +365,31 @@ struct akz_context {
     void* m_dbimg = nullptr;
     size_t m_qimg_cap = 0, m_dbimg_cap = 0;
     int match_path = AKZ_MATCH_AUTO;
+    // multi-GPU matching (akz_context_comm_init*, akz_match_top2_sharded*)
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_size = 1;
+    void* m_gather = nullptr;
+    size_t m_gather_cap = 0;
 };
+
+// live contexts by id: a handle that outlives its context must fail cleanly instead of touching freed memory
+static std::mutex g_registry_mu;
+static std::unordered_map<uint64_t, akz_context*> g_registry;
+static std::atomic<uint64_t> g_next_ctx_id{1};
+
+static akz_context* live_context(uint64_t id) {
+    std::lock_guard<std::mutex> g(g_registry_mu);
+    auto it = g_registry.find(id);
+    return it == g_registry.end() ? nullptr : it->second;
+}
 
 struct akz_features {
     akz_context* ctx = nullptr;
+    uint64_t ctx_id = 0;
     uint64_t generation = 0;
-    int img = 0, batch = 0;
+    int img = 0, batch = 0;            // index inside its pipeline sub-batch, images of that sub-batch
+    int lane = 0;                      // which set of work buffers the sub-batch used
+    uint32_t sub_batch_index = 0, n_sub_batches = 1;
     std::shared_ptr<PinnedChunk> chunk;                      // owns the memory kps/desc point into
     const akz_keypoint* kps = nullptr;
     const uint8_t* desc = nullptr;
@@ -387,6 +412,7 @@ static void free_results(Results& r) {
     r = Results();
 }
 static void free_buffers(akz_context* c) {
+    c->generation++;  // handles of earlier extractions must not read the freed planes
     free_lane(c->lane[0]);
     free_lane(c->lane[1]);
     free_results(c->res);
@@ -525,6 +551,13 @@ static int prepare(akz_context* c, uint32_t n, uint32_t w, uint32_t h, const akz
         free_buffers(c);
         c->plan = np;
         c->have_plan = true;
+        if (c->caps_auto) {
+            // the reference's Vec<Keypoint> has no capacity; the defaults follow the image size (one keypoint per 16
+            // pixels, four candidates per keypoint) so that a raw 3840x2160 frame works without akz_context_set_limits
+            const uint64_t px = (uint64_t)w * h;
+            c->kp_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(65536, (px / 16 + 4095) & ~4095ull), 1u << 22);
+            c->cand_cap = 4 * c->kp_cap;
+        }
         if (c->sub_batch_auto) {
             // Large sub-batches fill the GPU in the small octaves, give the latency-bound cache pass one warp per
             // image to hide behind and shorten the pipeline tail: up to 256 images per lane, as long as the two
@@ -812,9 +845,13 @@ static int collect_features(akz_context* c, uint32_t n, akz_features** outs) {
     for (uint32_t i = 0; i < n; i++) {
         std::unique_ptr<akz_features> f(new akz_features());
         f->ctx = c;
+        f->ctx_id = c->id;
         f->generation = c->generation;
-        f->img = (int)i;
-        f->batch = (int)n;
+        f->sub_batch_index = i / m;
+        f->n_sub_batches = (n + m - 1) / m;
+        f->lane = (int)(f->sub_batch_index & 1);
+        f->img = (int)(i % m);
+        f->batch = (int)std::min(m, n - f->sub_batch_index * m);
         f->levels = levels;
         f->desc_len = (uint32_t)c->plan.dev.desc_len;
         f->contrast = H.kcontrast[(size_t)i * kMaxLevels];
@@ -829,6 +866,8 @@ static int collect_features(akz_context* c, uint32_t n, akz_features** outs) {
     for (uint32_t i = 0; i < n; i++) outs[i] = fs[i].release();
     return AKZ_OK;
 }
+
+#define LOCK(c) std::lock_guard<std::recursive_mutex> lk__((c)->mu)
 
 extern "C" {
 
@@ -884,13 +923,25 @@ int akz_create(int device, uint32_t max_width, uint32_t max_height, uint32_t max
     CK(init_scale_space_attributes());
     CK(init_keypoint_attributes());
     CK(init_matcher_tc_attributes());
+    c->id = g_next_ctx_id.fetch_add(1);
+    {
+        std::lock_guard<std::mutex> g(g_registry_mu);
+        g_registry[c->id] = c.get();
+    }
     *out = c.release();
     return AKZ_OK;
 }
 
 void akz_destroy(akz_context* c) {
     if (!c) return;
+    {
+        std::lock_guard<std::mutex> g(g_registry_mu);
+        g_registry.erase(c->id);
+    }
+    { std::lock_guard<std::recursive_mutex> lk(c->mu); }  // let a call in flight on another thread finish
     cudaSetDevice(c->device);
+    if (c->comm) nccl_dyn::api().CommDestroy(c->comm);
+    cudaFree(c->m_gather);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->stream_kp);
     free_buffers(c);
@@ -926,12 +977,14 @@ uint64_t akz_context_launch_count(const akz_context* c) { return c ? c->launches
 
 int akz_context_enable_timing(akz_context* c, int enable) {
     if (!c) return fail(AKZ_ERR_INVALID, "null context");
+    LOCK(c);
     c->timing = enable != 0;
     return AKZ_OK;
 }
 
 int akz_context_stage_times(akz_context* c, double* ms, uint64_t* launches, int reset) {
     if (!c) return fail(AKZ_ERR_INVALID, "null context");
+    LOCK(c);
     for (int i = 0; i < AKZ_NUM_STAGES; i++) {
         if (ms) ms[i] = c->stage_ms[i];
         if (launches) launches[i] = c->stage_launches[i];
@@ -947,8 +1000,10 @@ int akz_context_set_limits(akz_context* c, uint32_t max_candidates, uint32_t max
     if (!c || max_candidates == 0 || max_keypoints == 0) return fail(AKZ_ERR_INVALID, "bad limits");
     if (max_keypoints > 0x7fffffffu) return fail(AKZ_ERR_INVALID, "max_keypoints too large");
     if (max_candidates < max_keypoints) max_candidates = max_keypoints;
+    LOCK(c);
     c->cand_cap = max_candidates;
     c->kp_cap = max_keypoints;
+    c->caps_auto = false;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->stream_kp);
@@ -958,12 +1013,14 @@ int akz_context_set_limits(akz_context* c, uint32_t max_candidates, uint32_t max
 
 int akz_context_set_match_path(akz_context* c, int path) {
     if (!c || path < AKZ_MATCH_AUTO || path > AKZ_MATCH_TENSOR) return fail(AKZ_ERR_INVALID, "bad match path");
+    LOCK(c);
     c->match_path = path;
     return AKZ_OK;
 }
 
 int akz_context_set_sub_batch(akz_context* c, uint32_t images) {
     if (!c || images == 0) return fail(AKZ_ERR_INVALID, "bad sub-batch size");
+    LOCK(c);
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->stream_kp);
@@ -974,8 +1031,9 @@ int akz_context_set_sub_batch(akz_context* c, uint32_t images) {
 
 int akz_extract_batch_u8(akz_context* c, uint32_t n, const uint8_t* const* grays, uint32_t w, uint32_t h, size_t stride,
                          const akz_config* cfg, akz_features** outs) {
-    if (!grays || !outs) return fail(AKZ_ERR_INVALID, "null argument");
+    if (!c || !grays || !outs) return fail(AKZ_ERR_INVALID, "null argument");
     if (stride < w) return fail(AKZ_ERR_INVALID, "stride < width");
+    LOCK(c);
     int rc = prepare(c, n, w, h, cfg);
     if (rc != AKZ_OK) return rc;
     // uploads run on their own stream, one event per pipeline sub-batch, so that the copy of sub-batch i+1
@@ -1005,7 +1063,8 @@ int akz_extract_u8(akz_context* c, const uint8_t* gray, uint32_t w, uint32_t h, 
 }
 
 int akz_extract_f32(akz_context* c, const float* unit_gray, uint32_t w, uint32_t h, const akz_config* cfg, akz_features** out) {
-    if (!unit_gray || !out) return fail(AKZ_ERR_INVALID, "null argument");
+    if (!c || !unit_gray || !out) return fail(AKZ_ERR_INVALID, "null argument");
+    LOCK(c);
     int rc = prepare(c, 1, w, h, cfg);
     if (rc != AKZ_OK) return rc;
     CK(cudaMemcpyAsync(c->res.in_f32, unit_gray, (size_t)w * h * sizeof(float), cudaMemcpyHostToDevice, c->stream));
@@ -1016,8 +1075,9 @@ int akz_extract_f32(akz_context* c, const float* unit_gray, uint32_t w, uint32_t
 
 int akz_extract_batch_u8_device(akz_context* c, uint32_t n, const void* d_grays, uint32_t w, uint32_t h, size_t stride,
                                 const akz_config* cfg, uint32_t* counts) {
-    if (!d_grays || !counts) return fail(AKZ_ERR_INVALID, "null argument");
+    if (!c || !d_grays || !counts) return fail(AKZ_ERR_INVALID, "null argument");
     if (stride < w) return fail(AKZ_ERR_INVALID, "stride < width");
+    LOCK(c);
     int rc = prepare(c, n, w, h, cfg);
     if (rc != AKZ_OK) return rc;
     rc = run_pipeline(c, n, d_grays, true, stride);
@@ -1029,7 +1089,9 @@ int akz_extract_batch_u8_device(akz_context* c, uint32_t n, const void* d_grays,
 }
 
 int akz_context_device_results(akz_context* c, void** d_keypoints, void** d_descriptors, uint32_t* kp_capacity) {
-    if (!c || !c->res.kps) return fail(AKZ_ERR_INVALID, "no extraction has run on this context");
+    if (!c) return fail(AKZ_ERR_INVALID, "null context");
+    LOCK(c);
+    if (!c->res.kps) return fail(AKZ_ERR_INVALID, "no extraction has run on this context");
     if (d_keypoints) *d_keypoints = c->res.kps;
     if (d_descriptors) *d_descriptors = c->res.desc;
     if (kp_capacity) *kp_capacity = c->kp_cap;
@@ -1058,11 +1120,20 @@ uint64_t akz_features_num_cache(const akz_features* f) { return f ? f->n_cache :
 
 int akz_features_evolution_download(const akz_features* f, uint32_t level, int kind, float* dst) {
     if (!f || !dst || level >= f->levels->size()) return fail(AKZ_ERR_INVALID, "bad argument");
-    akz_context* c = f->ctx;
-    if (!(c->flags & AKZ_KEEP_EVOLUTIONS)) return fail(AKZ_ERR_INVALID, "context was created without AKZ_KEEP_EVOLUTIONS");
-    if (c->generation != f->generation) return fail(AKZ_ERR_INVALID, "evolutions were overwritten by a later extraction");
+    akz_context* c = live_context(f->ctx_id);
+    if (!c || c != f->ctx) return fail(AKZ_ERR_INVALID, "the context of these features has been destroyed");
+    LOCK(c);
+    if (c->generation != f->generation) return fail(AKZ_ERR_INVALID, "evolutions were overwritten by a later extraction (or the context's buffers were resized)");
+    const bool keep = (c->flags & AKZ_KEEP_EVOLUTIONS) != 0;
+    // Without AKZ_KEEP_EVOLUTIONS only the four planes the keypoint stages sample (Lt, Lx, Ly, Ldet; Lsmooth_0 is Lt_0,
+    // lib.rs:58) are persistent, and only for the images of the last sub-batch on each of the two work-buffer lanes.
+    if (!keep) {
+        const bool plane_kept = kind == AKZ_LT || kind == AKZ_LX || kind == AKZ_LY || kind == AKZ_LDET || (kind == AKZ_LSMOOTH && level == 0);
+        if (!plane_kept) return fail(AKZ_ERR_INVALID, "only Lt, Lx, Ly and Ldet stay resident without AKZ_KEEP_EVOLUTIONS");
+        if (f->sub_batch_index + 2 < f->n_sub_batches) return fail(AKZ_ERR_INVALID, "the evolutions of this image were overwritten by a later sub-batch of the same call");
+    }
     CK(cudaSetDevice(c->device));
-    const Buffers& B = c->lane[0].buf;  // keep-evolutions mode runs the whole call as one sub-batch on lane 0
+    const Buffers& B = c->lane[f->lane].buf;  // keep-evolutions mode runs the whole call as one sub-batch on lane 0
     const float* plane = nullptr;
     switch (kind) {
         case AKZ_LT: plane = B.Lt; break;
@@ -1078,6 +1149,7 @@ int akz_features_evolution_download(const akz_features* f, uint32_t level, int k
         default: return fail(AKZ_ERR_INVALID, "bad image kind");
     }
     if (level == 0 && (kind == AKZ_LFLOW || kind == AKZ_LSTEP)) return fail(AKZ_ERR_INVALID, "level 0 has no Lflow/Lstep (0x0 in the reference)");
+    if (!plane) return fail(AKZ_ERR_INVALID, "image plane is not resident");
     const LevelDev& lv = c->plan.dev.lv[level];
     const size_t px = (size_t)lv.w * lv.h;
     const float* src = plane + (size_t)lv.off * f->batch + (size_t)f->img * px;
@@ -1103,6 +1175,7 @@ int akz_match_top2_device(akz_context* c, const void* d_q, uint64_t nq, const vo
                           void* d_out) {
     if (!c || (nq && (!d_q || !d_out)) || (ndb && !d_db)) return fail(AKZ_ERR_INVALID, "null argument");
     if (nq == 0) return AKZ_OK;
+    LOCK(c);
     if (ndb > 0xffffffffull || nq > 0xffffffffull) return fail(AKZ_ERR_CAPACITY, "more than 2^32 descriptors");
     CK(cudaSetDevice(c->device));
     // tensor-core path (matcher_tc.cu) unless the problem is too small to amortise the 64 KB operand tiles
@@ -1131,6 +1204,7 @@ int akz_match_top2_device(akz_context* c, const void* d_q, uint64_t nq, const vo
 
 int akz_merge_top2_device(akz_context* c, const void* d_parts, uint32_t n_parts, uint64_t nq, void* d_out) {
     if (!c || (nq && (!d_parts || !d_out)) || n_parts == 0) return fail(AKZ_ERR_INVALID, "bad argument");
+    LOCK(c);
     CK(cudaSetDevice(c->device));
     c->launches += launch_merge_top2(c->stream, (const akz_top2*)d_parts, n_parts, nq, (akz_top2*)d_out);
     CK(cudaGetLastError());
@@ -1156,6 +1230,7 @@ int akz_match_top2(akz_context* c, const uint8_t* q, uint64_t nq, const uint8_t*
     if (!c || (nq && (!q || !out)) || (ndb && !db)) return fail(AKZ_ERR_INVALID, "null argument");
     if (desc_len == 0 || desc_len > (uint32_t)kDescStride || stride < desc_len) return fail(AKZ_ERR_INVALID, "desc_len must be 1..64 and <= stride");
     if (nq == 0) return AKZ_OK;
+    LOCK(c);
     CK(cudaSetDevice(c->device));
     int rc = upload_padded(c, q, nq, desc_len, stride, &c->m_q, &c->m_q_cap);
     if (rc != AKZ_OK) return rc;
@@ -1174,16 +1249,20 @@ int akz_descriptor_match(akz_context* c, const uint8_t* d0, uint64_t n0, const u
                          size_t stride, uint64_t distance_threshold, double lowes_ratio, akz_match* out, uint64_t* n_out) {
     if (!n_out || (n0 && !out)) return fail(AKZ_ERR_INVALID, "null argument");
     *n_out = 0;
-    if (distance_threshold != 10000) return fail(AKZ_ERR_INVALID, "distance_threshold is hard-wired to 10000 (akaze/src/lib.rs:264)");
     std::vector<akz_top2> t(n0);
     int rc = akz_match_top2(c, d0, n0, d1, n1, desc_len, stride, t.data());
     if (rc != AKZ_OK) return rc;
+    // feature_matching.rs:38-50 seeds min and second-to-min with distance_threshold T: the pair it ends up with is the two
+    // smallest values of {d_j} U {T, T}. The device seeds with 10000 (lib.rs:264), far above any Hamming distance of 64
+    // bytes, so its (best, second) are the true two smallest distances whenever they exist; re-seeding with T is a min().
+    const uint64_t T = distance_threshold;
     const double r2 = lowes_ratio * lowes_ratio;  // powi(2), feature_matching.rs:61
     uint64_t k = 0;
     for (uint64_t i = 0; i < n0; i++) {
-        const uint64_t mn = t[i].best, sc = t[i].second;
+        const uint64_t d_best = n1 >= 1 ? t[i].best : UINT64_MAX, d_second = n1 >= 2 ? t[i].second : UINT64_MAX;
+        const uint64_t mn = std::min(d_best, T), sc = std::min(d_second, T);
         if ((double)mn < (double)sc * r2) {
-            if (mn < distance_threshold) {
+            if (mn < T) {  // then mn is a real distance and best_idx the lowest index attaining it
                 out[k].index_0 = i;
                 out[k].index_1 = t[i].best_idx;
                 out[k].distance = (double)mn;
@@ -1192,6 +1271,167 @@ int akz_descriptor_match(akz_context* c, const uint8_t* d0, uint64_t n0, const u
         }
     }
     *n_out = k;
+    return AKZ_OK;
+}
+
+// ---- multi-GPU matching -------------------------------------------------------
+// The database is partitioned contiguously by index over the ranks (one context per GPU), the queries are replicated.
+// Every rank computes its shard's top-2 records, the 8-byte records are all-gathered with NCCL over NVLink (8 MB per
+// rank per 1 M queries) and merged with the sequential scan's tie rule (lowest database index wins), so every rank
+// ends up with the result of the unsharded scan (feature_matching.rs:37-50), bit for bit.
+#define NCK(call)                                                                                             \
+    do {                                                                                                      \
+        ncclResult_t r__ = (call);                                                                            \
+        if (r__ != 0) return fail(AKZ_ERR_CUDA, std::string(#call) + ": " + nccl_dyn::api().GetErrorString(r__)); \
+    } while (0)
+
+static int need_nccl() {
+    if (!nccl_dyn::api().ok()) return fail(AKZ_ERR_CUDA, nccl_dyn::api().error);
+    return AKZ_OK;
+}
+
+int akz_comm_unique_id(uint8_t* id) {
+    if (!id) return fail(AKZ_ERR_INVALID, "null id");
+    int rc = need_nccl();
+    if (rc != AKZ_OK) return rc;
+    ncclUniqueId u;
+    NCK(nccl_dyn::api().GetUniqueId(&u));
+    static_assert(sizeof(u) == AKZ_COMM_UNIQUE_ID_BYTES, "ncclUniqueId is 128 bytes");
+    memcpy(id, &u, sizeof(u));
+    return AKZ_OK;
+}
+
+static int drop_comm(akz_context* c) {
+    if (c->comm) {
+        CK(cudaSetDevice(c->device));
+        CK(cudaStreamSynchronize(c->stream));
+        nccl_dyn::api().CommDestroy(c->comm);
+        c->comm = nullptr;
+    }
+    c->comm_rank = 0;
+    c->comm_size = 1;
+    return AKZ_OK;
+}
+
+int akz_context_comm_init(akz_context* c, const uint8_t* id, int rank, int n_ranks) {
+    if (!c || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(AKZ_ERR_INVALID, "bad communicator arguments");
+    int rc = need_nccl();
+    if (rc != AKZ_OK) return rc;
+    LOCK(c);
+    rc = drop_comm(c);
+    if (rc != AKZ_OK) return rc;
+    CK(cudaSetDevice(c->device));
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof(u));
+    NCK(nccl_dyn::api().CommInitRank(&c->comm, n_ranks, u, rank));
+    c->comm_rank = rank;
+    c->comm_size = n_ranks;
+    return AKZ_OK;
+}
+
+int akz_context_comm_init_all(akz_context* const* ctxs, int n) {
+    if (!ctxs || n < 1) return fail(AKZ_ERR_INVALID, "bad communicator arguments");
+    int rc = need_nccl();
+    if (rc != AKZ_OK) return rc;
+    std::vector<int> devs(n);
+    for (int i = 0; i < n; i++) {
+        if (!ctxs[i]) return fail(AKZ_ERR_INVALID, "null context");
+        for (int j = 0; j < i; j++)
+            if (ctxs[j]->device == ctxs[i]->device) return fail(AKZ_ERR_INVALID, "one context per device, please");
+        rc = drop_comm(ctxs[i]);
+        if (rc != AKZ_OK) return rc;
+        devs[i] = ctxs[i]->device;
+    }
+    std::vector<ncclComm_t> comms(n, nullptr);
+    NCK(nccl_dyn::api().CommInitAll(comms.data(), n, devs.data()));
+    for (int i = 0; i < n; i++) {
+        ctxs[i]->comm = comms[i];
+        ctxs[i]->comm_rank = i;
+        ctxs[i]->comm_size = n;
+    }
+    return AKZ_OK;
+}
+
+int akz_context_comm_destroy(akz_context* c) {
+    if (!c) return fail(AKZ_ERR_INVALID, "null context");
+    LOCK(c);
+    return drop_comm(c);
+}
+
+// the three phases of one rank's share; the single-process driver below interleaves them over its contexts
+static int sharded_match_phase(akz_context* c, const void* d_q, uint64_t nq, const void* d_db_shard, uint64_t ndb_shard, uint32_t db_index_base) {
+    int rc = grow(&c->m_gather, &c->m_gather_cap, (size_t)(c->comm_size + 1) * nq * sizeof(akz_top2));
+    if (rc != AKZ_OK) return rc;
+    akz_top2* mine = (akz_top2*)c->m_gather + (size_t)c->comm_size * nq;  // this rank's records, behind the gathered ones
+    // an empty shard (more ranks than descriptors) yields the seeds {10000, 10000}: the popc kernel runs zero tiles
+    return akz_match_top2_device(c, d_q, nq, d_db_shard, ndb_shard, db_index_base, mine);
+}
+static int sharded_gather_phase(akz_context* c, uint64_t nq) {
+    const akz_top2* mine = (const akz_top2*)c->m_gather + (size_t)c->comm_size * nq;
+    NCK(nccl_dyn::api().AllGather(mine, c->m_gather, nq * sizeof(akz_top2), nccl_dyn::kUint8, c->comm, c->stream));
+    return AKZ_OK;
+}
+static int sharded_merge_phase(akz_context* c, uint64_t nq, void* d_out) {
+    return akz_merge_top2_device(c, c->m_gather, (uint32_t)c->comm_size, nq, d_out);  // ranks are ordered by database index range
+}
+
+int akz_match_top2_sharded_device(akz_context* c, const void* d_q, uint64_t nq, const void* d_db_shard, uint64_t ndb_shard,
+                                  uint32_t db_index_base, void* d_out) {
+    if (!c || (nq && (!d_q || !d_out)) || (ndb_shard && !d_db_shard)) return fail(AKZ_ERR_INVALID, "null argument");
+    LOCK(c);
+    if (!c->comm) return fail(AKZ_ERR_INVALID, "no communicator: call akz_context_comm_init first");
+    if (nq == 0) return AKZ_OK;
+    CK(cudaSetDevice(c->device));
+    int rc = sharded_match_phase(c, d_q, nq, d_db_shard, ndb_shard, db_index_base);
+    if (rc != AKZ_OK) return rc;
+    rc = sharded_gather_phase(c, nq);
+    if (rc != AKZ_OK) return rc;
+    return sharded_merge_phase(c, nq, d_out);
+}
+
+int akz_match_top2_sharded(akz_context* const* ctxs, int n_gpu, const uint8_t* q, uint64_t nq, const uint8_t* db, uint64_t ndb,
+                           uint32_t desc_len, size_t stride, akz_top2* out) {
+    if (!ctxs || n_gpu < 1 || (nq && (!q || !out)) || (ndb && !db)) return fail(AKZ_ERR_INVALID, "null argument");
+    if (desc_len == 0 || desc_len > (uint32_t)kDescStride || stride < desc_len) return fail(AKZ_ERR_INVALID, "desc_len must be 1..64 and <= stride");
+    for (int i = 0; i < n_gpu; i++)
+        if (!ctxs[i] || !ctxs[i]->comm || ctxs[i]->comm_size != n_gpu || ctxs[i]->comm_rank != i)
+            return fail(AKZ_ERR_INVALID, "contexts must share a communicator of n_gpu ranks (akz_context_comm_init_all), in rank order");
+    if (nq == 0) return AKZ_OK;
+    const uint64_t per = (ndb + (uint64_t)n_gpu - 1) / (uint64_t)n_gpu;  // contiguous shards by index
+    std::vector<std::unique_lock<std::recursive_mutex>> locks;
+    for (int i = 0; i < n_gpu; i++) locks.emplace_back(ctxs[i]->mu);
+    int rc;
+    for (int i = 0; i < n_gpu; i++) {  // uploads + shard kernels: asynchronous on every device's own stream
+        akz_context* c = ctxs[i];
+        const uint64_t lo = std::min(ndb, (uint64_t)i * per), hi = std::min(ndb, lo + per);
+        CK(cudaSetDevice(c->device));
+        rc = upload_padded(c, q, nq, desc_len, stride, &c->m_q, &c->m_q_cap);
+        if (rc != AKZ_OK) return rc;
+        rc = upload_padded(c, db + lo * stride, hi - lo, desc_len, stride, &c->m_db, &c->m_db_cap);
+        if (rc != AKZ_OK) return rc;
+        rc = sharded_match_phase(c, c->m_q, nq, c->m_db, hi - lo, (uint32_t)lo);
+        if (rc != AKZ_OK) return rc;
+    }
+    NCK(nccl_dyn::api().GroupStart());  // one thread drives all ranks: the collective must be issued as a group
+    for (int i = 0; i < n_gpu; i++) {
+        rc = sharded_gather_phase(ctxs[i], nq);
+        if (rc != AKZ_OK) {
+            nccl_dyn::api().GroupEnd();
+            return rc;
+        }
+    }
+    NCK(nccl_dyn::api().GroupEnd());
+    akz_context* c0 = ctxs[0];
+    CK(cudaSetDevice(c0->device));
+    rc = grow(&c0->m_out, &c0->m_out_cap, (size_t)nq * sizeof(akz_top2));
+    if (rc != AKZ_OK) return rc;
+    rc = sharded_merge_phase(c0, nq, c0->m_out);
+    if (rc != AKZ_OK) return rc;
+    CK(cudaMemcpyAsync(out, c0->m_out, (size_t)nq * sizeof(akz_top2), cudaMemcpyDeviceToHost, c0->stream));
+    for (int i = 0; i < n_gpu; i++) {
+        CK(cudaSetDevice(ctxs[i]->device));
+        CK(cudaStreamSynchronize(ctxs[i]->stream));
+    }
     return AKZ_OK;
 }
 

@@ -23,17 +23,39 @@ def _is_json(path):
     return os.path.splitext(str(path))[1].lower() == ".json"
 
 
-def features_to_bytes(keypoints, descriptors, desc_len=61):
-    """keypoints: structured array with x, y, response, size, octave, class_id, angle; descriptors: (n, >= desc_len) u8."""
+def _descriptor_rows(descriptors, n, desc_len):
+    """Descriptor.vector of every keypoint as its own u8 array. The reference serialises each vector with its own
+    length (akaze-util/src/lib.rs:11-14: Vec<Descriptor>), i.e. (162*channels+7)/8 = 21 / 41 / 61 bytes for
+    descriptor_channels 1 / 2 / 3; desc_len=None takes the width of the array that is passed."""
+    if n == 0:
+        return []
+    if isinstance(descriptors, np.ndarray) and descriptors.ndim == 2:
+        d = np.asarray(descriptors, np.uint8)
+        return list(d[:, :desc_len] if desc_len else d)
+    rows = [np.asarray(r, np.uint8).ravel() for r in descriptors]
+    return [r[:desc_len] for r in rows] if desc_len else rows
+
+
+def features_to_bytes(keypoints, descriptors, desc_len=None):
+    """keypoints: structured array with x, y, response, size, octave, class_id, angle; descriptors: (n, len) u8 array or a
+    list of u8 arrays."""
     n = len(keypoints)
     k = np.zeros(n, KP_BIN)
     for f in KP_BIN.names:
         k[f] = keypoints[f]
-    d = np.ascontiguousarray(np.asarray(descriptors, np.uint8).reshape(n, -1)[:, :desc_len]) if n else np.zeros((0, desc_len), np.uint8)
-    rows = np.zeros(n, np.dtype([("len", "<u8"), ("bytes", "u1", (desc_len,))]))
-    rows["len"] = desc_len
-    rows["bytes"] = d
-    return np.uint64(n).tobytes() + k.tobytes() + np.uint64(n).tobytes() + rows.tobytes()
+    rows = _descriptor_rows(descriptors, n, desc_len)
+    if len(rows) != n:
+        raise ValueError("%d keypoints but %d descriptors" % (n, len(rows)))
+    lens = {len(r) for r in rows}
+    if len(lens) == 1:  # the usual case: one dense block
+        ln = lens.pop()
+        blk = np.zeros(n, np.dtype([("len", "<u8"), ("bytes", "u1", (ln,))]))
+        blk["len"] = ln
+        blk["bytes"] = np.stack(rows) if ln else np.zeros((n, 0), np.uint8)
+        body = blk.tobytes()
+    else:
+        body = b"".join(np.uint64(len(r)).tobytes() + np.ascontiguousarray(r).tobytes() for r in rows)
+    return np.uint64(n).tobytes() + k.tobytes() + np.uint64(n).tobytes() + body
 
 
 def features_from_bytes(b):
@@ -71,12 +93,13 @@ def _f32(v):
     return json.loads(str(np.float32(v)))  # shortest decimal that round-trips the f32
 
 
-def serialize_features_to_file(keypoints, descriptors, path, desc_len=61):
+def serialize_features_to_file(keypoints, descriptors, path, desc_len=None):
     """akaze-util serialize_features_to_file (lib.rs:17-30)."""
     if _is_json(path):
+        descriptors = _descriptor_rows(descriptors, len(keypoints), desc_len)
         doc = {"keypoints": [{"point": [_f32(k["x"]), _f32(k["y"])], "response": _f32(k["response"]), "size": _f32(k["size"]),
                               "octave": int(k["octave"]), "class_id": int(k["class_id"]), "angle": _f32(k["angle"])} for k in keypoints],
-               "descriptors": [{"vector": [int(v) for v in np.asarray(d, np.uint8)[:desc_len]]} for d in descriptors]}
+               "descriptors": [{"vector": [int(v) for v in d]} for d in descriptors]}
         with open(path, "w") as fh:
             json.dump(doc, fh, separators=(",", ":"))
     else:

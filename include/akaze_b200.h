@@ -9,8 +9,11 @@
  * Conventions: every function returns an int status (AKZ_OK == 0); akz_last_error() gives a
  * thread-local message for the last failure on the calling thread. Inputs are caller-owned plain
  * buffers; outputs are either caller-provided buffers or library-owned handles released with the
- * matching akz_*_free. A context is bound to one CUDA device and is safe to use from one thread
- * at a time. There is NO CPU fallback: every entry point that computes fails with AKZ_ERR_CUDA if
+ * matching akz_*_free. A context is bound to one CUDA device. Thread safety: every entry point that
+ * takes a context locks it, so one context may be shared by several threads (calls are serialised
+ * per context; use one context per thread or per GPU for concurrency); akz_features accessors only
+ * read host memory owned by the handle and need no lock; akz_last_error() is per thread.
+ * There is NO CPU fallback: every entry point that computes fails with AKZ_ERR_CUDA if
  * no usable sm_100 device is present.
  */
 #ifndef AKAZE_B200_H
@@ -120,7 +123,9 @@ int akz_context_enable_timing(akz_context *ctx, int enable);
 int akz_context_stage_times(akz_context *ctx, double *ms, uint64_t *launches, int reset);
 /* Per-image capacities of the candidate list (4-neighbour maxima inside the descriptor margin) and of
  * the keypoint cache; exceeding either makes the extraction fail with AKZ_ERR_CAPACITY instead of
- * truncating. Defaults: 262144 candidates, 65536 keypoints. Call before the first extraction. */
+ * truncating (the reference's Vec<Keypoint> is unbounded, scale_space_extrema.rs:17). Defaults follow the
+ * image size: max(65536, pixels / 16) keypoints and four times as many candidates (a raw 3840x2160 frame
+ * gets 518400 / 2073600); this call pins them instead. Call before the first extraction. */
 int akz_context_set_limits(akz_context *ctx, uint32_t max_candidates, uint32_t max_keypoints);
 
 /* A call of n images is cut into sub-batches of `images` that flow through a two-stage software pipeline
@@ -170,8 +175,11 @@ double akz_features_contrast_factor(const akz_features *f); /* contrast_factor.r
 /* candidate / cache statistics of find_scale_space_extrema (scale_space_extrema.rs:12-132) */
 uint64_t akz_features_num_candidates(const akz_features *f);
 uint64_t akz_features_num_cache(const akz_features *f);
-/* Copies one image of one EvolutionStep (width*height floats) to dst. Needs AKZ_KEEP_EVOLUTIONS and
- * must be called before the next extraction on the same context. */
+/* Copies one image of one EvolutionStep (width*height floats) to dst; must be called before the next
+ * extraction on the same context (AKZ_ERR_INVALID afterwards, or once the context is destroyed). All ten
+ * images need AKZ_KEEP_EVOLUTIONS. Without it the four planes the keypoint stages sample -- Lt, Lx, Ly, Ldet
+ * (and Lsmooth of level 0, which is Lt_0, lib.rs:58) -- are still served, for the images of the last two
+ * pipeline sub-batches of the call (every image of a call of up to 2 x sub-batch images). */
 int akz_features_evolution_download(const akz_features *f, uint32_t level, int kind, float *dst);
 void akz_features_free(akz_features *f);
 
@@ -190,10 +198,35 @@ int akz_match_top2_device(akz_context *ctx, const void *d_q, uint64_t nq, const 
  * index range); d_out: akz_top2[nq]. Same tie rule as the sequential scan (lowest index wins). */
 int akz_merge_top2_device(akz_context *ctx, const void *d_parts, uint32_t n_parts, uint64_t nq, void *d_out);
 /* descriptor_match proper: top-2 on the device, then the f64 Lowe-ratio and threshold tests
- * (feature_matching.rs:61-80) on the host. out must hold n0 entries; *n_out receives the count. */
+ * (feature_matching.rs:61-80) on the host, for any distance_threshold (akaze::match_features passes
+ * 10000, lib.rs:264). out must hold n0 entries; *n_out receives the count. */
 int akz_descriptor_match(akz_context *ctx, const uint8_t *d0, uint64_t n0, const uint8_t *d1, uint64_t n1,
                          uint32_t desc_len, size_t stride, uint64_t distance_threshold, double lowes_ratio,
                          akz_match *out, uint64_t *n_out);
+
+/* ---- multi-GPU matching: the database is partitioned contiguously by index over the
+ *      GPUs, queries are replicated, every GPU runs the top-2 scan on its shard, the 8-byte records are
+ *      all-gathered with NCCL over NVLink and merged with the sequential scan's tie rule (lowest index),
+ *      so the result equals descriptor_match's unsharded scan (feature_matching.rs:37-50) bit for bit.
+ *      NCCL (libnccl.so.2) is bound at run time; environment AKZ_NCCL_LIB overrides the library path. */
+#define AKZ_COMM_UNIQUE_ID_BYTES 128
+/* ncclGetUniqueId: call on one rank, ship the 128 bytes to the others by any means. */
+int akz_comm_unique_id(uint8_t *id);
+/* One process (or thread) per GPU: joins this context to a communicator of n_ranks (ncclCommInitRank). */
+int akz_context_comm_init(akz_context *ctx, const uint8_t *id, int rank, int n_ranks);
+/* One process driving n GPUs: a communicator over n contexts on n distinct devices (ncclCommInitAll);
+ * ctxs[i] becomes rank i. */
+int akz_context_comm_init_all(akz_context *const *ctxs, int n);
+int akz_context_comm_destroy(akz_context *ctx);
+/* Per rank, device buffers: d_db_shard holds the rank's slice [db_index_base, db_index_base + ndb_shard)
+ * of the database (rank order = ascending index order), d_q all nq queries; shard scan, ncclAllGather
+ * and merge are issued on the context's stream; every rank's d_out receives akz_top2[nq]. */
+int akz_match_top2_sharded_device(akz_context *ctx, const void *d_q, uint64_t nq, const void *d_db_shard,
+                                  uint64_t ndb_shard, uint32_t db_index_base, void *d_out);
+/* Single-process form with host buffers: shards db over the n_gpu contexts of one communicator
+ * (akz_context_comm_init_all), out[nq] as akz_match_top2. */
+int akz_match_top2_sharded(akz_context *const *ctxs, int n_gpu, const uint8_t *q, uint64_t nq, const uint8_t *db,
+                           uint64_t ndb, uint32_t desc_len, size_t stride, akz_top2 *out);
 
 #ifdef __cplusplus
 }

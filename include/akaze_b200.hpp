@@ -110,7 +110,8 @@ struct EvolutionStep {
 
 [[noreturn]] inline void fail(const char* what) { throw std::runtime_error(std::string(what) + ": " + akz_last_error()); }
 
-// One engine per thread (a context is single-threaded by contract); RAII over akz_context.
+// RAII over akz_context. The library serialises calls per context (see the thread-safety note in akaze_b200.h), so one
+// Engine may be shared between threads; use one per thread or per GPU for concurrency.
 class Engine {
 public:
     explicit Engine(int device = 0, uint32_t max_width = 4096, uint32_t max_height = 4096, uint32_t max_batch = 1, bool keep_evolutions = false) {

@@ -1,0 +1,91 @@
+"""CPU-only checks of the host layer (no compute calls): on-disk formats for every descriptor width, gray-image loading,
+argument validation that must not reach the library, the C ABI's symbol list."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _features(akz, n, width, seed=0):
+    rng = np.random.default_rng(seed)
+    k = np.zeros(n, akz.KEYPOINT_DTYPE)
+    k["x"], k["y"] = rng.uniform(0, 640, n), rng.uniform(0, 480, n)
+    k["response"], k["size"], k["angle"] = rng.uniform(0, 0.1, n), 4.8, rng.uniform(0, 3.1, n)
+    k["octave"], k["class_id"] = rng.integers(0, 4, n), rng.integers(0, 16, n)
+    return k, rng.integers(0, 256, (n, width), dtype=np.uint8)
+
+
+@pytest.mark.parametrize("channels", [1, 2, 3])
+def test_feature_files_for_every_descriptor_width(akz, tmp_path, channels):
+    """Descriptor.vector has (162*channels+7)/8 = 21 / 41 / 61 bytes (descriptors.rs:42-46) and akaze-util writes each
+    vector with its own length (akaze-util/src/lib.rs:11-30): bincode and JSON round trips for all three widths."""
+    from akaze_rust_b200 import formats
+    width = (162 * channels + 7) // 8
+    k, d = _features(akz, 9, width, seed=channels)
+    b = formats.features_to_bytes(k, d)
+    assert len(b) == 8 + 9 * 36 + 8 + 9 * (8 + width)
+    k2, d2 = formats.features_from_bytes(b)
+    assert np.array_equal(np.stack(d2), d) and np.array_equal(k2["x"], k["x"]) and np.array_equal(k2["class_id"], k["class_id"])
+    for ext in ("bin", "json"):
+        p = tmp_path / ("f." + ext)
+        formats.serialize_features_to_file(k, d, str(p))
+        k3, d3 = formats.deserialize_features_from_file(str(p))
+        assert all(len(v) == width for v in d3) and np.array_equal(np.stack(d3), d)
+        assert np.array_equal(k3["angle"], k["angle"]) and np.array_equal(k3["octave"], k["octave"])
+    # the engine's padded 64-byte rows cut to the descriptor length
+    pad = np.zeros((9, 64), np.uint8)
+    pad[:, :width] = d
+    assert formats.features_to_bytes(k, pad, width) == b
+    # ragged vectors (a list) keep their own lengths
+    rag = [d[i][: 1 + i] for i in range(9)]
+    k4, d4 = formats.features_from_bytes(formats.features_to_bytes(k, rag))
+    assert [len(v) for v in d4] == [1 + i for i in range(9)]
+    with pytest.raises(ValueError):
+        formats.features_to_bytes(k, d[:5])
+
+
+def test_load_gray_keeps_gray_sources_unchanged(akz, tmp_path):
+    """image::open + to_luma (lib.rs:171, image.rs:128): Luma8 sources pass through unchanged (to_luma is the identity
+    there); only RGB sources go through the Rec.709 weights."""
+    from PIL import Image
+    ramp = np.tile(np.arange(256, dtype=np.uint8), (4, 1))
+    p = tmp_path / "ramp.png"
+    Image.fromarray(ramp).save(p)
+    assert np.array_equal(akz.load_gray(str(p)), ramp)  # all 256 gray levels survive
+    rgb = np.stack([ramp, ramp, ramp], axis=-1)
+    q = tmp_path / "ramp_rgb.png"
+    Image.fromarray(rgb).save(q)
+    g = akz.load_gray(str(q))
+    assert g.shape == ramp.shape and np.abs(g.astype(int) - ramp.astype(int)).max() <= 1  # truncating f32 weights
+    assert np.array_equal(akz.to_luma_u8(ramp), ramp)
+
+
+def test_header_and_bindings_agree(akz):
+    """Every function include/akaze_b200.h declares is bound by the host layer and exported by the library."""
+    import ctypes
+    hdr = open(os.path.join(ROOT, "include", "akaze_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(akz_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(akz.EXPORTS), declared ^ set(akz.EXPORTS)
+    L = ctypes.CDLL(akz.LIB_PATH)
+    for name in declared:
+        assert hasattr(L, name), name
+    for name in ("akz_comm_unique_id", "akz_context_comm_init", "akz_context_comm_init_all", "akz_match_top2_sharded_device", "akz_match_top2_sharded"):
+        assert name in declared
+
+
+def test_argument_validation_needs_no_gpu(akz):
+    e = akz.Engine.__new__(akz.Engine)  # no context: the checks below must fire before the library is called
+    e._h = None
+    with pytest.raises(ValueError):
+        e.extract_u8(np.zeros((32, 64, 3), np.uint8))
+    with pytest.raises(ValueError):
+        e.extract_batch_u8([np.zeros((32, 64), np.uint8), np.zeros((32, 65), np.uint8)])
+    with pytest.raises(ValueError):
+        e.descriptor_match(np.zeros((3, 64), np.uint8), np.zeros((3, 61), np.uint8))
+    with pytest.raises(ValueError):
+        e.match_top2(np.zeros((3, 65), np.uint8), np.zeros((3, 65), np.uint8))
+    assert e.extract_batch_u8([]) == []
