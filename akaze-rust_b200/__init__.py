@@ -213,11 +213,22 @@ class Features:
         self._h = handle
         self._engine = engine  # keeps the engine alive while its evolutions can still be downloaded
         self.count = int(L.akz_features_count(handle))
-        self.descriptor_len = L.akz_features_descriptor_len(handle)
-        self.contrast_factor = L.akz_features_contrast_factor(handle)
-        self.num_candidates = L.akz_features_num_candidates(handle)
-        self.num_cache = L.akz_features_num_cache(handle)
+        self._meta = None      # the other scalars are fetched on first use (a 1024-image batch creates 1024 of these)
         self._kp = self._desc = self._evo = None
+
+    def _scalars(self):
+        if self._meta is None:
+            L, h = lib(), self._h
+            if not h:
+                raise AkazeError(1, "features were released before their metadata was read")
+            self._meta = (L.akz_features_descriptor_len(h), L.akz_features_contrast_factor(h), L.akz_features_num_candidates(h),
+                          L.akz_features_num_cache(h))
+        return self._meta
+
+    descriptor_len = property(lambda self: self._scalars()[0])
+    contrast_factor = property(lambda self: self._scalars()[1])
+    num_candidates = property(lambda self: self._scalars()[2])
+    num_cache = property(lambda self: self._scalars()[3])
 
     # keypoints / descriptors are copied out of the library-owned (pinned) buffers on first access, so the
     # arrays stay valid after close(); `count` is free
@@ -280,7 +291,7 @@ class Features:
     def close(self):
         if self._h:
             # materialise what callers may still read after close (cheap; evolutions' images are not kept)
-            self.keypoints, self.descriptors_padded, self.evolutions  # noqa: B018
+            self._scalars(), self.keypoints, self.descriptors_padded, self.evolutions  # noqa: B018
             lib().akz_features_free(self._h)
             self._h = None
 

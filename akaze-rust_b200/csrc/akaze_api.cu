@@ -263,6 +263,9 @@ std::string build_plan(uint32_t w, uint32_t h, const akz_config& cfg, Plan* P) {
     while ((((int)w >> D.grid_shift) + 1) * (((int)h >> D.grid_shift) + 1) > 8448) D.grid_shift++;
     D.grid_w = ((int)w >> D.grid_shift) + 1;
     D.grid_h = ((int)h >> D.grid_shift) + 1;
+    // cache-pass pools: room for the candidates of the busiest level (a photo-like 1080p frame has ~2 k per level, a
+    // 3840x2160 one ~10 k); images beyond it take the global-memory pass
+    D.pool_cap = (int)std::min<uint64_t>(64512, std::max<uint64_t>(4096, (((uint64_t)w * h / 384) + 1023) & ~1023ull));
     return "";
 }
 
@@ -347,6 +350,7 @@ struct akz_context {
     Results res;
     int cur_batch = 0;
     uint32_t n_sub_batches = 0;
+    std::vector<std::pair<uint32_t, uint32_t>> sched;  // (first image, count) of every sub-batch of the current call
     // per-stage timing
     bool timing = false;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pool;
@@ -470,7 +474,7 @@ static int ensure_lane(akz_context* c, Lane& ln, int batch) {
     CK(dalloc(A, &B.c_cls, kc));
     CK(dalloc(A, &B.c_next, kc));
     CK(dalloc(A, &B.grid, nb * 2 * (size_t)P.dev.grid_w * P.dev.grid_h));
-    CK(dalloc(A, &B.dedup_pool, nb * dedup_pool_bytes()));
+    CK(dalloc(A, &B.dedup_pool, nb * dedup_pool_bytes(P)));
     CK(dalloc(A, &B.keep_flag, kc));
     CK(dalloc(A, &B.cls_range, nb * kMaxLevels * 2));
     CK(dalloc(A, &B.plan_dev, 1));
@@ -516,15 +520,39 @@ static int ensure_results(akz_context* c, int n) {
     return AKZ_OK;
 }
 
-static bool same_cfg(const akz_config& a, const akz_config& b) { return memcmp(&a, &b, sizeof(akz_config)) == 0; }
-
 // images per sub-batch for a call of n images
 static uint32_t sub_batch_of(const akz_context* c, uint32_t n) {
     if (c->flags & AKZ_KEEP_EVOLUTIONS) return n;  // evolutions of every image of the call stay resident
     return std::min(n, c->sub_batch);
 }
 
-static int prepare(akz_context* c, uint32_t n, uint32_t w, uint32_t h, const akz_config* cfg) {
+// The sub-batches of a call of n images. Device-resident inputs: equal sub-batches of `sub_batch` images. Host inputs:
+// the first sub-batch's upload and the last one's result download cannot hide behind anything, so the schedule ramps
+// up (m/4, m/2, m, m, ...) and ends on a short sub-batch; uploads run at about twice the extraction rate at 1080p, which
+// is what a doubling ramp needs to keep the kernels fed.
+static void make_schedule(akz_context* c, uint32_t n, bool host_io) {
+    c->sched.clear();
+    const uint32_t m = sub_batch_of(c, n);
+    static const bool no_ramp = getenv("AKZ_NO_RAMP") != nullptr;  // A/B switch
+    if (!host_io || no_ramp || (c->flags & AKZ_KEEP_EVOLUTIONS) || n < 8) {
+        for (uint32_t i0 = 0; i0 < n; i0 += m) c->sched.push_back({i0, std::min(m, n - i0)});
+        return;
+    }
+    const uint32_t tail = std::max<uint32_t>(1u, std::min<uint32_t>(m / 4, n / 8));
+    uint32_t i0 = 0, step = tail;
+    while (i0 < n - tail) {
+        const uint32_t cnt = std::min(step, n - tail - i0);
+        c->sched.push_back({i0, cnt});
+        i0 += cnt;
+        step = std::min<uint32_t>(m, step * 2);
+    }
+    c->sched.push_back({i0, n - i0});
+}
+
+static bool same_cfg(const akz_config& a, const akz_config& b) { return memcmp(&a, &b, sizeof(akz_config)) == 0; }
+
+
+static int prepare(akz_context* c, uint32_t n, uint32_t w, uint32_t h, const akz_config* cfg, bool host_io) {
     if (!c || !cfg) return fail(AKZ_ERR_INVALID, "null argument");
     if (n == 0) return fail(AKZ_ERR_INVALID, "empty batch");
     if (n > c->max_batch) return fail(AKZ_ERR_CAPACITY, "batch larger than the context's max_batch");
@@ -566,15 +594,17 @@ static int prepare(akz_context* c, uint32_t n, uint32_t w, uint32_t h, const akz
             CK(cudaMemGetInfo(&free_b, &total_b));
             const size_t n0 = (size_t)w * h;
             const size_t per_image = 4 * (4 * (size_t)np.dev.plane_px + 3 * n0) + 4 * (size_t)np.dev.mask_words + 4 * (size_t)c->cand_cap +
-                                     40 * (size_t)c->kp_cap + dedup_pool_bytes() + (1 << 16);
+                                     40 * (size_t)c->kp_cap + dedup_pool_bytes(np) + (1 << 16);
             const size_t fit = (free_b / 2) / (2 * per_image);
             c->sub_batch = (uint32_t)std::max<size_t>(16, std::min<size_t>(256, fit));
         }
     }
-    const uint32_t m = sub_batch_of(c, n);
+    make_schedule(c, n, host_io);
+    uint32_t m = 0;  // the largest sub-batch of the call: what a lane of work buffers must hold
+    for (const auto& sb : c->sched) m = std::max(m, sb.second);
     int rc = ensure_lane(c, c->lane[0], (int)m);
     if (rc != AKZ_OK) return rc;
-    if (n > m) {
+    if (c->sched.size() > 1) {
         rc = ensure_lane(c, c->lane[1], (int)m);
         if (rc != AKZ_OK) return rc;
     }
@@ -624,7 +654,6 @@ static void harvest_timing(akz_context* c) {
 static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8, size_t in_stride, bool wait_copies = false) {
     const Plan& P = c->plan;
     const Results& R = c->res;
-    const uint32_t m = sub_batch_of(c, n);
     c->generation++;
     c->cur_batch = (int)n;
     const size_t in_img = in_stride * P.h * (is_u8 ? 1 : sizeof(float));  // bytes per input image
@@ -675,9 +704,9 @@ static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8
         CK(cudaEventRecord(c->ev_stats[pd.sb], c->stream_kp));
         return AKZ_OK;
     };
-    for (uint32_t i0 = 0, sb = 0; i0 < n; i0 += m, sb++) {
+    for (uint32_t sb = 0; sb < (uint32_t)c->sched.size(); sb++) {
         Lane& ln = c->lane[sb & 1];
-        const uint32_t cnt = std::min(m, n - i0);
+        const uint32_t i0 = c->sched[sb].first, cnt = c->sched[sb].second;
         if (ln.busy) CK(cudaStreamWaitEvent(c->stream, ln.ev_done, 0));  // the lane's previous sub-batch must be through stage B
         if (wait_copies) CK(cudaStreamWaitEvent(c->stream, c->ev_copy[sb], 0));  // its inputs must have arrived
         Buffers B = ln.buf;
@@ -707,7 +736,7 @@ static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8
         // four-warp blocks that still fit beside it) and not next to the descriptor kernel, whose four 256-thread blocks
         // need the whole register file of an SM: with a cache-pass warp resident only three fit (measured: descriptors
         // +22 %, filter/orientation +20 %). The last sub-batch has nothing behind it, so its cache pass goes first.
-        const bool last = (i0 + m >= n);
+        const bool last = (sb + 1 == (uint32_t)c->sched.size());
         auto launch_cache_pass = [&]() -> int {
             CK(cudaStreamWaitEvent(c->stream_kp, ln.ev_stencil, 0));
             if (have_prev && !last) CK(cudaStreamWaitEvent(c->stream_kp, prev.ln->ev_done, 0));
@@ -740,7 +769,7 @@ static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8
         int rc = finish_sub_batch(prev);
         if (rc != AKZ_OK) return rc;
     }
-    c->n_sub_batches = (n + m - 1) / m;
+    c->n_sub_batches = (uint32_t)c->sched.size();
 #undef STAGE
     for (int l = 0; l < 2; l++)
         if (c->lane[l].busy) {
@@ -798,15 +827,14 @@ static int get_chunk(akz_context* c, size_t bytes, std::shared_ptr<PinnedChunk>*
 static int collect_features(akz_context* c, uint32_t n, akz_features** outs) {
     const Results& R = c->res;
     const HostStats& H = c->hs;
-    const uint32_t m = sub_batch_of(c, n);
     struct Slot {
         std::shared_ptr<PinnedChunk> chunk;
         size_t kp_off, desc_off;
     };
     std::vector<Slot> slots(n);
     int rc = AKZ_OK;
-    for (uint32_t i0 = 0, sb = 0; i0 < n && rc == AKZ_OK; i0 += m, sb++) {
-        const uint32_t i1 = std::min(n, i0 + m);
+    for (uint32_t sb = 0; sb < (uint32_t)c->sched.size() && rc == AKZ_OK; sb++) {
+        const uint32_t i0 = c->sched[sb].first, i1 = i0 + c->sched[sb].second;
         CK(cudaEventSynchronize(c->ev_stats[sb]));
         rc = check_err_flags(c, i0, i1);
         if (rc != AKZ_OK) break;
@@ -842,16 +870,18 @@ static int collect_features(akz_context* c, uint32_t n, akz_features** outs) {
     CK(e3);
     auto levels = std::make_shared<const std::vector<LevelHost>>(c->plan.host);
     std::vector<std::unique_ptr<akz_features>> fs;
+    uint32_t sb_of = 0;
     for (uint32_t i = 0; i < n; i++) {
+        while (i >= c->sched[sb_of].first + c->sched[sb_of].second) sb_of++;
         std::unique_ptr<akz_features> f(new akz_features());
         f->ctx = c;
         f->ctx_id = c->id;
         f->generation = c->generation;
-        f->sub_batch_index = i / m;
-        f->n_sub_batches = (n + m - 1) / m;
-        f->lane = (int)(f->sub_batch_index & 1);
-        f->img = (int)(i % m);
-        f->batch = (int)std::min(m, n - f->sub_batch_index * m);
+        f->sub_batch_index = sb_of;
+        f->n_sub_batches = (uint32_t)c->sched.size();
+        f->lane = (int)(sb_of & 1);
+        f->img = (int)(i - c->sched[sb_of].first);
+        f->batch = (int)c->sched[sb_of].second;
         f->levels = levels;
         f->desc_len = (uint32_t)c->plan.dev.desc_len;
         f->contrast = H.kcontrast[(size_t)i * kMaxLevels];
@@ -1034,13 +1064,13 @@ int akz_extract_batch_u8(akz_context* c, uint32_t n, const uint8_t* const* grays
     if (!c || !grays || !outs) return fail(AKZ_ERR_INVALID, "null argument");
     if (stride < w) return fail(AKZ_ERR_INVALID, "stride < width");
     LOCK(c);
-    int rc = prepare(c, n, w, h, cfg);
+    int rc = prepare(c, n, w, h, cfg, true);
     if (rc != AKZ_OK) return rc;
     // uploads run on their own stream, one event per pipeline sub-batch, so that the copy of sub-batch i+1
     // overlaps the kernels of sub-batch i (asynchronous when the caller's images are in pinned memory)
-    const uint32_t m = sub_batch_of(c, n);
-    for (uint32_t i0 = 0, sb = 0; i0 < n; i0 += m, sb++) {
-        for (uint32_t i = i0; i < std::min(n, i0 + m); i++) {
+    for (uint32_t sb = 0; sb < (uint32_t)c->sched.size(); sb++) {
+        const uint32_t i0 = c->sched[sb].first;
+        for (uint32_t i = i0; i < i0 + c->sched[sb].second; i++) {
             if (!grays[i]) return fail(AKZ_ERR_INVALID, "null image");
             CK(cudaMemcpy2DAsync(c->res.in_u8 + (size_t)i * w * h, w, grays[i], stride, w, h, cudaMemcpyHostToDevice, c->stream_copy));
         }
@@ -1065,7 +1095,7 @@ int akz_extract_u8(akz_context* c, const uint8_t* gray, uint32_t w, uint32_t h, 
 int akz_extract_f32(akz_context* c, const float* unit_gray, uint32_t w, uint32_t h, const akz_config* cfg, akz_features** out) {
     if (!c || !unit_gray || !out) return fail(AKZ_ERR_INVALID, "null argument");
     LOCK(c);
-    int rc = prepare(c, 1, w, h, cfg);
+    int rc = prepare(c, 1, w, h, cfg, false);
     if (rc != AKZ_OK) return rc;
     CK(cudaMemcpyAsync(c->res.in_f32, unit_gray, (size_t)w * h * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     rc = run_pipeline(c, 1, c->res.in_f32, false, w);
@@ -1078,7 +1108,7 @@ int akz_extract_batch_u8_device(akz_context* c, uint32_t n, const void* d_grays,
     if (!c || !d_grays || !counts) return fail(AKZ_ERR_INVALID, "null argument");
     if (stride < w) return fail(AKZ_ERR_INVALID, "stride < width");
     LOCK(c);
-    int rc = prepare(c, n, w, h, cfg);
+    int rc = prepare(c, n, w, h, cfg, false);
     if (rc != AKZ_OK) return rc;
     rc = run_pipeline(c, n, d_grays, true, stride);
     if (rc != AKZ_OK) return rc;

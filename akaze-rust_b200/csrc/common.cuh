@@ -55,6 +55,7 @@ struct PlanDev {
     int n_orient_windows;
     int grid_shift;        // dedup hash grid: cell = 1<<grid_shift full-resolution pixels
     int grid_w, grid_h;
+    int pool_cap;          // entries per class-parity pool of the cache pass (per image)
     LevelDev lv[kMaxLevels];
 };
 
@@ -156,7 +157,7 @@ int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level)
 int launch_compact(const Launch& L, const Plan& P, const Buffers& B);
 // keypoints.cu
 cudaError_t init_keypoint_attributes();
-size_t dedup_pool_bytes();
+size_t dedup_pool_bytes(const Plan& P);
 int launch_dedup(const Launch& L, const Plan& P, const Buffers& B);
 int launch_finalize(const Launch& L, const Plan& P, const Buffers& B);
 int launch_descriptors(const Launch& L, const Plan& P, const Buffers& B);

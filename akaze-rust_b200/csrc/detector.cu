@@ -404,6 +404,19 @@ __device__ __forceinline__ void h_neighbours(const float (&v)[4], float (&ext)[1
     for (int j = 0; j < S; j++) ext[8 + j] = __shfl_down_sync(0xffffffffu, v[j], 1);
 }
 
+// out[j] = er[j] - el[j]: for even S the operands pair up as they sit in their float4 registers (packed FSUB2, neither
+// operand is a product); for odd S column j and j+1 straddle two float4s and a packed form would need moves
+template <int S>
+__device__ __forceinline__ void diff4(const float (&er)[4], const float (&el)[4], float (&out)[4]) {
+    if (S % 2 == 0) {
+        sub2(er[0], er[1], el[0], el[1], out[0], out[1]);
+        sub2(er[2], er[3], el[2], el[3], out[2], out[3]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; j++) out[j] = er[j] - el[j];
+    }
+}
+
 // Row c of the pipeline. STEADY: every stage is active, no ring read clamps, no border rows to replicate,
 // -> no row tests besides the three warp-uniform flags of DetSteadyPtrs (stores / candidate test on or off), and the ring
 // handles of rows c and c-S (which rows c-2S and c-3S share) come in as sl[0..1], advanced by the caller.
@@ -566,8 +579,7 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
         {
             const float el[4] = {e[4 - S], e[5 - S], e[6 - S], e[7 - S]}, er[4] = {e[4 + S], e[5 + S], e[6 + S], e[7 + S]};
             tap3x4(n, wn, n, el, v, er, R.a);
-#pragma unroll
-            for (int j = 0; j < 4; j++) R.bo[j] = er[j] - el[j];
+            diff4<S>(er, el, R.bo);
         }
         det_fix_cols<S, BORDER>(k, R.a);
         det_fix_cols<S, BORDER>(k, R.bo);
@@ -578,7 +590,8 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
         const int rm = STEADY ? s0 : rg.uniform(rg.handle(max(o1 - S, k.ylo) % D));  // row c - 2S shares the slot of row c
         float4 a_m = rg.template load<0>(rm), b_m = rg.template load<1>(rm), b_0 = rg.template load<1>(s1);
         rg.fence3(a_m, b_m, b_0);
-        R.lx[0] = R.a[0] - a_m.x; R.lx[1] = R.a[1] - a_m.y; R.lx[2] = R.a[2] - a_m.z; R.lx[3] = R.a[3] - a_m.w;
+        sub2(R.a[0], R.a[1], a_m.x, a_m.y, R.lx[0], R.lx[1]);  // A is a sum, a_m comes out of the ring: nothing to contract
+        sub2(R.a[2], R.a[3], a_m.z, a_m.w, R.lx[2], R.lx[3]);
         {
             const float bm[4] = {b_m.x, b_m.y, b_m.z, b_m.w}, b0[4] = {b_0.x, b_0.y, b_0.z, b_0.w};
             tap3x4(n, wn, n, bm, b0, R.bo, R.ly);
@@ -604,12 +617,13 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
         {
             const float el[4] = {e[4 - S], e[5 - S], e[6 - S], e[7 - S]}, er[4] = {e[4 + S], e[5 + S], e[6 + S], e[7 + S]};
             tap3x4(n, wn, n, el, R.lx, er, R.cc);
-#pragma unroll
-            for (int j = 0; j < 4; j++) R.ee[j] = er[j] - el[j];
+            diff4<S>(er, el, R.ee);
         }
         h_neighbours<S>(R.ly, e);
-#pragma unroll
-        for (int j = 0; j < 4; j++) R.dd[j] = e[4 + j + S] - e[4 + j - S];
+        {
+            const float el[4] = {e[4 - S], e[5 - S], e[6 - S], e[7 - S]}, er[4] = {e[4 + S], e[5 + S], e[6 + S], e[7 + S]};
+            diff4<S>(er, el, R.dd);
+        }
         det_fix_cols<S, BORDER>(k, R.cc);
         det_fix_cols<S, BORDER>(k, R.ee);
         det_fix_cols<S, BORDER>(k, R.dd);
@@ -626,15 +640,23 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
         float lyy4[4], lxy4[4];
         tap3x4(n, wn, n, dm, d0, R.dd, lyy4);
         tap3x4(n, wn, n, em, e0, R.ee, lxy4);
+        // Ldet = ((Lxx * Lyy) - (Lxy * Lxy)) * s^4 (detector_response.rs:52): Lxx = C - C_m and the three products packed in
+        // pairs, the one subtraction of products scalar
+        float lxx4[4], p1[4], p2[4], df[4];
+        sub2(R.cc[0], R.cc[1], cm[0], cm[1], lxx4[0], lxx4[1]);
+        sub2(R.cc[2], R.cc[3], cm[2], cm[3], lxx4[2], lxx4[3]);
+        mul2v(lxx4[0], lxx4[1], lyy4[0], lyy4[1], p1[0], p1[1]);
+        mul2v(lxx4[2], lxx4[3], lyy4[2], lyy4[3], p1[2], p1[3]);
+        mul2v(lxy4[0], lxy4[1], lxy4[0], lxy4[1], p2[0], p2[1]);
+        mul2v(lxy4[2], lxy4[3], lxy4[2], lxy4[3], p2[2], p2[3]);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-            const float lxx = R.cc[j] - cm[j];
-            const float lyy = lyy4[j];
-            const float lxy = lxy4[j];
+            df[j] = p1[j] - p2[j];
             R.det_m[j] = R.det_0[j];
             R.det_0[j] = R.det_p[j];
-            R.det_p[j] = ((lxx * lyy) - (lxy * lxy)) * k.quat;  // detector_response.rs:52
         }
+        mul2(df[0], df[1], k.quat, R.det_p[0], R.det_p[1]);
+        mul2(df[2], df[3], k.quat, R.det_p[2], R.det_p[3]);
         if (STEADY) {
             if (k.xout && sp.st2) st4(sp.pd, make_float4(R.det_p[0], R.det_p[1], R.det_p[2], R.det_p[3]));
         } else {

@@ -164,7 +164,6 @@ k_dedup(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ cand,
 // slot) when its class falls out of reach. Hash-grid heads are u16 pool indices. An image whose
 // busiest level has more than kPool candidates is left to the global-memory kernel above.
 // ------------------------------------------------------------------------------------------------
-constexpr int kPool = 4096;
 constexpr int kGroups = 8;   // candidates decided per step of the cache pass (lanes per candidate = 32 / kGroups)
 constexpr int kMaxGridCells = 8448;
 constexpr unsigned short kNil = 0xffffu;
@@ -172,7 +171,7 @@ constexpr unsigned short kNil = 0xffffu;
 __device__ __forceinline__ bool image_fits_smem_pass(const PlanDev* plan, const unsigned int* lo) {
     if (plan->grid_w * plan->grid_h > kMaxGridCells) return false;
     for (int l = 0; l < plan->n_levels; l++)
-        if (lo[l + 1] - lo[l] > (unsigned int)kPool) return false;
+        if (lo[l + 1] - lo[l] > (unsigned int)plan->pool_cap) return false;
     return true;
 }
 
@@ -184,22 +183,38 @@ __device__ __forceinline__ bool image_fits_smem_pass(const PlanDev* plan, const 
 struct DedupSmem {
     unsigned short heads[2][kMaxGridCells];
 };
+// per-image slab of dedup_pool_bytes(): two pools (class parity) of plan.pool_cap entries each; pool_cap follows the image
+// size (PlanDev::pool_cap, <= 65534 because pool indices are u16) so that a 3840x2160 frame's busiest level fits too
 struct DedupPool {
-    float px[2][kPool];
-    float py[2][kPool];
-    float presp[2][kPool];
-    unsigned int pslot[2][kPool];  // global cache slot; 0xffffffff = dead (replaced)
-    unsigned short pnext[2][kPool];
+    float* px[2];
+    float* py[2];
+    float* presp[2];
+    unsigned int* pslot[2];  // global cache slot; 0xffffffff = dead (replaced)
+    unsigned short* pnext[2];
+    __device__ __forceinline__ DedupPool(unsigned char* slab, int cap) {
+        float* f = reinterpret_cast<float*>(slab);
+        px[0] = f;
+        px[1] = f + cap;
+        py[0] = f + 2 * cap;
+        py[1] = f + 3 * cap;
+        presp[0] = f + 4 * cap;
+        presp[1] = f + 5 * cap;
+        pslot[0] = reinterpret_cast<unsigned int*>(f + 6 * cap);
+        pslot[1] = pslot[0] + cap;
+        pnext[0] = reinterpret_cast<unsigned short*>(f + 8 * cap);
+        pnext[1] = pnext[0] + cap;
+    }
 };
+constexpr size_t kPoolBytesPerEntry = 8 * 4 + 2 * 2;
 
 __global__ void __launch_bounds__(32)
 k_dedup_smem(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ cand, const unsigned int* __restrict__ level_off,
              const float* __restrict__ ldet_plane, int batch, unsigned int cand_cap, unsigned int kp_cap, float* __restrict__ c_x,
              float* __restrict__ c_y, float* __restrict__ c_resp, int* __restrict__ c_cls, unsigned int* __restrict__ n_cache,
-             unsigned int* __restrict__ err_flags, DedupPool* pools) {
+             unsigned int* __restrict__ err_flags, unsigned char* pools) {
     __shared__ DedupSmem S;
     const int img = blockIdx.x;
-    DedupPool& G = pools[img];
+    const DedupPool G(pools + (size_t)img * ((size_t)plan->pool_cap * kPoolBytesPerEntry), plan->pool_cap);
     const int lane = threadIdx.x;
     const unsigned int FULL = 0xffffffffu;
     const unsigned int* cl = cand + (size_t)img * cand_cap;
@@ -344,7 +359,7 @@ k_dedup_smem(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ 
                 }
                 if (commits && act != 0) {
                     const unsigned int slot = (act == 1) ? n + __popc(amask & lt) : best;
-                    const int at = cnt[cur] + __popc(wmask & lt);  // <= candidates of this level <= kPool
+                    const int at = cnt[cur] + __popc(wmask & lt);  // <= candidates of this level <= pool_cap
                     if (act == 2) G.pslot[bw][be] = 0xffffffffu;  // the old occupant is dead; it stays on its cell list
                     G.px[cur][at] = fx;
                     G.py[cur][at] = fy;
@@ -817,12 +832,12 @@ cudaError_t init_keypoint_attributes() {
     return cudaFuncSetAttribute(k_dedup, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
-size_t dedup_pool_bytes() { return sizeof(DedupPool); }
+size_t dedup_pool_bytes(const Plan& P) { return (size_t)P.dev.pool_cap * kPoolBytesPerEntry; }
 
 int launch_dedup(const Launch& L, const Plan& P, const Buffers& B) {
     // every image is handled by exactly one of the two kernels (image_fits_smem_pass)
     k_dedup_smem<<<L.batch, 32, 0, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap, L.kp_cap, B.c_x,
-                                               B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags, (DedupPool*)B.dedup_pool);
+                                               B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags, B.dedup_pool);
     k_dedup<<<L.batch, 32, 0, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap, L.kp_cap,
                                            B.c_x, B.c_y, B.c_resp, B.c_cls, B.c_next, B.grid, B.n_cache, B.err_flags);
     return 2;

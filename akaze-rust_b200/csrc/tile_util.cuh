@@ -39,6 +39,26 @@ __device__ __forceinline__ void mul2v(float a0, float a1, float b0, float b1, fl
         : "=f"(p0), "=f"(p1)
         : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
+// Packed f32x2 add / subtract (FADD2): only for operands that are NOT products computed in the same straight-line code
+// (loaded, shuffled, loop-carried or themselves sums) -- ptxas would contract a packed product + packed add into FFMA2.
+__device__ __forceinline__ void add2(float a0, float a1, float b0, float b1, float& r0, float& r1) {
+    asm("{.reg .b64 ra, rb, rr;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "add.rn.f32x2 rr, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rr;}"
+        : "=f"(r0), "=f"(r1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void sub2(float a0, float a1, float b0, float b1, float& r0, float& r1) {
+    asm("{.reg .b64 ra, rb, rr;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "sub.rn.f32x2 rr, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rr;}"
+        : "=f"(r0), "=f"(r1)
+        : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
 // out[j] = (k0 * a[j] + k1 * b[j]) + k2 * c[j], j = 0..3, in tap order (products packed in pairs, sums scalar)
 __device__ __forceinline__ void tap3x4(float k0, float k1, float k2, const float (&a)[4], const float (&b)[4], const float (&c)[4],
                                        float (&out)[4]) {

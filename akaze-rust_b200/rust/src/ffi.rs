@@ -51,6 +51,26 @@ pub struct akz_level_info {
 }
 
 pub const AKZ_KEEP_EVOLUTIONS: u32 = 1;
+pub const AKZ_DESCRIPTOR_STRIDE: usize = 64;
+// enum akz_image_kind
+pub const AKZ_LT: c_int = 0;
+pub const AKZ_LSMOOTH: c_int = 1;
+pub const AKZ_LX: c_int = 2;
+pub const AKZ_LY: c_int = 3;
+pub const AKZ_LXX: c_int = 4;
+pub const AKZ_LYY: c_int = 5;
+pub const AKZ_LXY: c_int = 6;
+pub const AKZ_LFLOW: c_int = 7;
+pub const AKZ_LSTEP: c_int = 8;
+pub const AKZ_LDET: c_int = 9;
+
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct akz_top2 {
+    pub best_idx: u32,
+    pub best: u16,
+    pub second: u16,
+}
 
 extern "C" {
     pub fn akz_last_error() -> *const c_char;
@@ -70,4 +90,10 @@ extern "C" {
     pub fn akz_descriptor_match(ctx: *mut c_void, d0: *const u8, n0: u64, d1: *const u8, n1: u64, desc_len: u32,
                                 stride: usize, distance_threshold: u64, lowes_ratio: f64, out: *mut akz_match,
                                 n_out: *mut u64) -> c_int;
+    pub fn akz_match_top2(ctx: *mut c_void, q: *const u8, nq: u64, db: *const u8, ndb: u64, desc_len: u32, stride: usize,
+                          out: *mut akz_top2) -> c_int;
+    // multi-GPU matching: one context per device, NCCL all-gather + merge inside the library
+    pub fn akz_context_comm_init_all(ctxs: *const *mut c_void, n: c_int) -> c_int;
+    pub fn akz_match_top2_sharded(ctxs: *const *mut c_void, n_gpu: c_int, q: *const u8, nq: u64, db: *const u8, ndb: u64,
+                                  desc_len: u32, stride: usize, out: *mut akz_top2) -> c_int;
 }

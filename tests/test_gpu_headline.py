@@ -192,4 +192,4 @@ def test_cli_debug_dir_on_the_engine(akz, tmp_path):
     rc = cli.main(["extract_features", str(p), str(tmp_path / "out.bin"), "-d", str(tmp_path / "dbg")])
     assert rc == 0
     names = sorted(os.listdir(tmp_path / "dbg"))
-    assert "Lt_00.npy" in names and "Ldet_15.npy" in names and "Lflow_01.npy" in names and "Lflow_00.npy" not in names
+    assert "Lt_00.npy" in names and "Ldet_11.npy" in names and "Ldet_12.npy" not in names and "Lflow_01.npy" in names and "Lflow_00.npy" not in names

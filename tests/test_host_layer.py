@@ -89,3 +89,23 @@ def test_argument_validation_needs_no_gpu(akz):
     with pytest.raises(ValueError):
         e.match_top2(np.zeros((3, 65), np.uint8), np.zeros((3, 65), np.uint8))
     assert e.extract_batch_u8([]) == []
+
+
+def test_rust_overlay_lists_every_source_and_symbol(akz):
+    """The Rust overlay cannot be compiled here; at least keep it honest: build.rs names every CUDA source build.py
+    compiles, every extern "C" function ffi.rs declares exists in the header, lib.rs only calls functions ffi.rs declares."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("akz_build", os.path.join(ROOT, "akaze-rust_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    rust = os.path.join(ROOT, "akaze-rust_b200", "rust")
+    build_rs = open(os.path.join(rust, "build.rs")).read()
+    assert sorted(re.findall(r'"(\w+\.cu)"', build_rs)) == sorted(b.SOURCES)
+    ffi = open(os.path.join(rust, "src", "ffi.rs")).read()
+    declared = set(re.findall(r"pub fn (akz_\w+)", ffi))
+    assert declared and declared <= set(akz.EXPORTS), declared - set(akz.EXPORTS)
+    lib_rs = open(os.path.join(rust, "src", "lib.rs")).read()
+    assert set(re.findall(r"ffi::(akz_[a-z0-9_]+)\(", lib_rs)) <= declared
+    for const in set(re.findall(r"ffi::(AKZ_\w+)", lib_rs)):
+        assert re.search(r"pub const %s\b" % const, ffi), const
+    assert not os.path.exists(os.path.join(rust, "src", "types")) and "download_all(f" in lib_rs and "unsafe fn download_all" in lib_rs
