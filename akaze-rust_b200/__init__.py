@@ -400,17 +400,30 @@ class Engine:
         return Features(out, self)
 
     def extract_batch_u8(self, grays, config=None):
-        grays = [_gray2d(g, np.uint8) for g in grays]
-        n = len(grays)
-        if n == 0:
-            return []
-        h, w = grays[0].shape
-        if any(g.shape != (h, w) for g in grays):
-            raise ValueError("all images of a batch must have the same size")
+        """n images of one size: a list of 2-D uint8 arrays, or one C-contiguous (n, h, w) uint8 array (the cheap form for
+        large batches: no per-image Python work, and the library uploads each pipeline sub-batch as a single copy)."""
         cfg = config or Config.default()
-        ptrs = (C.c_void_p * n)(*[g.ctypes.data for g in grays])
+        if isinstance(grays, np.ndarray) and grays.ndim == 3:
+            if grays.dtype != np.uint8 or not grays.flags.c_contiguous:
+                grays = np.ascontiguousarray(grays, np.uint8)
+            n, h, w = grays.shape
+            if n == 0:
+                return []
+            addr = grays.ctypes.data + np.arange(n, dtype=np.uint64) * np.uint64(h * w)
+            ptrs = (C.c_void_p * n).from_buffer(addr)
+            keep = grays
+        else:
+            keep = [_gray2d(g, np.uint8) for g in grays]
+            n = len(keep)
+            if n == 0:
+                return []
+            h, w = keep[0].shape
+            if any(g.shape != (h, w) for g in keep):
+                raise ValueError("all images of a batch must have the same size")
+            ptrs = (C.c_void_p * n)(*[g.ctypes.data for g in keep])
         outs = (C.c_void_p * n)()
         _check(lib().akz_extract_batch_u8(self._h, n, ptrs, w, h, w, C.byref(cfg), outs))
+        del keep
         return [Features(C.c_void_p(o), self) for o in outs]
 
     def extract_batch_u8_device(self, d_ptr, n, width, height, stride=None, config=None):

@@ -15,6 +15,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <unordered_map>
@@ -266,6 +267,11 @@ std::string build_plan(uint32_t w, uint32_t h, const akz_config& cfg, Plan* P) {
     // cache-pass pools: room for the candidates of the busiest level (a photo-like 1080p frame has ~2 k per level, a
     // 3840x2160 one ~10 k); images beyond it take the global-memory pass
     D.pool_cap = (int)std::min<uint64_t>(64512, std::max<uint64_t>(4096, (((uint64_t)w * h / 384) + 1023) & ~1023ull));
+    // level-pipelined cache pass: u16 heads of one grid per level in shared memory, at most ~72 KB per image
+    D.lgrid_shift = 4;
+    while ((size_t)nl * ((w >> D.lgrid_shift) + 1) * ((h >> D.lgrid_shift) + 1) * 2 > 72 * 1024) D.lgrid_shift++;
+    D.lgrid_w = ((int)w >> D.lgrid_shift) + 1;
+    D.lgrid_h = ((int)h >> D.lgrid_shift) + 1;
     return "";
 }
 
@@ -475,6 +481,7 @@ static int ensure_lane(akz_context* c, Lane& ln, int batch) {
     CK(dalloc(A, &B.c_next, kc));
     CK(dalloc(A, &B.grid, nb * 2 * (size_t)P.dev.grid_w * P.dev.grid_h));
     CK(dalloc(A, &B.dedup_pool, nb * dedup_pool_bytes(P)));
+    CK(dalloc(A, &B.level_pool, nb * dedup_level_pool_bytes(c->cand_cap)));
     CK(dalloc(A, &B.keep_flag, kc));
     CK(dalloc(A, &B.cls_range, nb * kMaxLevels * 2));
     CK(dalloc(A, &B.plan_dev, 1));
@@ -594,7 +601,7 @@ static int prepare(akz_context* c, uint32_t n, uint32_t w, uint32_t h, const akz
             CK(cudaMemGetInfo(&free_b, &total_b));
             const size_t n0 = (size_t)w * h;
             const size_t per_image = 4 * (4 * (size_t)np.dev.plane_px + 3 * n0) + 4 * (size_t)np.dev.mask_words + 4 * (size_t)c->cand_cap +
-                                     40 * (size_t)c->kp_cap + dedup_pool_bytes(np) + (1 << 16);
+                                     40 * (size_t)c->kp_cap + dedup_pool_bytes(np) + dedup_level_pool_bytes(c->cand_cap) + (1 << 16);
             const size_t fit = (free_b / 2) / (2 * per_image);
             c->sub_batch = (uint32_t)std::max<size_t>(16, std::min<size_t>(256, fit));
         }
@@ -651,7 +658,11 @@ static void harvest_timing(akz_context* c) {
 
 // runs the whole pipeline on inputs already in device memory; results stay on the device (c->res).
 // On return everything has been ISSUED and c->stream waits for all of it.
-static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8, size_t in_stride, bool wait_copies = false) {
+// `upload`, when given, enqueues the host -> device copy of one sub-batch on the copy stream and records ev_copy[sb]; it is
+// called one sub-batch ahead of the kernels that consume it.
+static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8, size_t in_stride,
+                        const std::function<int(uint32_t)>& upload = nullptr) {
+    const bool wait_copies = (bool)upload;
     const Plan& P = c->plan;
     const Results& R = c->res;
     c->generation++;
@@ -704,9 +715,17 @@ static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8
         CK(cudaEventRecord(c->ev_stats[pd.sb], c->stream_kp));
         return AKZ_OK;
     };
+    if (upload) {
+        int rc = upload(0);
+        if (rc != AKZ_OK) return rc;
+    }
     for (uint32_t sb = 0; sb < (uint32_t)c->sched.size(); sb++) {
         Lane& ln = c->lane[sb & 1];
         const uint32_t i0 = c->sched[sb].first, cnt = c->sched[sb].second;
+        if (upload && sb + 1 < (uint32_t)c->sched.size()) {
+            int rc = upload(sb + 1);
+            if (rc != AKZ_OK) return rc;
+        }
         if (ln.busy) CK(cudaStreamWaitEvent(c->stream, ln.ev_done, 0));  // the lane's previous sub-batch must be through stage B
         if (wait_copies) CK(cudaStreamWaitEvent(c->stream, c->ev_copy[sb], 0));  // its inputs must have arrived
         Buffers B = ln.buf;
@@ -1066,22 +1085,31 @@ int akz_extract_batch_u8(akz_context* c, uint32_t n, const uint8_t* const* grays
     LOCK(c);
     int rc = prepare(c, n, w, h, cfg, true);
     if (rc != AKZ_OK) return rc;
-    // uploads run on their own stream, one event per pipeline sub-batch, so that the copy of sub-batch i+1
-    // overlaps the kernels of sub-batch i (asynchronous when the caller's images are in pinned memory)
-    for (uint32_t sb = 0; sb < (uint32_t)c->sched.size(); sb++) {
-        const uint32_t i0 = c->sched[sb].first;
-        for (uint32_t i = i0; i < i0 + c->sched[sb].second; i++) {
-            if (!grays[i]) return fail(AKZ_ERR_INVALID, "null image");
-            CK(cudaMemcpy2DAsync(c->res.in_u8 + (size_t)i * w * h, w, grays[i], stride, w, h, cudaMemcpyHostToDevice, c->stream_copy));
+    // uploads run on their own stream, one event per pipeline sub-batch, so that the copy of sub-batch i+1 overlaps the
+    // kernels of sub-batch i (asynchronous when the caller's images are in pinned memory); images that follow each other
+    // in host memory without row padding travel as ONE copy per sub-batch
+    for (uint32_t i = 0; i < n; i++)
+        if (!grays[i]) return fail(AKZ_ERR_INVALID, "null image");
+    auto upload = [&](uint32_t sb) -> int {
+        const uint32_t i0 = c->sched[sb].first, cnt = c->sched[sb].second;
+        const size_t img = (size_t)w * h;
+        bool contiguous = stride == w;
+        for (uint32_t i = i0 + 1; contiguous && i < i0 + cnt; i++) contiguous = grays[i] == grays[i - 1] + img;
+        if (contiguous) {
+            CK(cudaMemcpyAsync(c->res.in_u8 + (size_t)i0 * img, grays[i0], (size_t)cnt * img, cudaMemcpyHostToDevice, c->stream_copy));
+        } else {
+            for (uint32_t i = i0; i < i0 + cnt; i++)
+                CK(cudaMemcpy2DAsync(c->res.in_u8 + (size_t)i * img, w, grays[i], stride, w, h, cudaMemcpyHostToDevice, c->stream_copy));
         }
-        if (c->ev_copy.size() <= sb) {
+        while (c->ev_copy.size() <= sb) {
             cudaEvent_t e;
             CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             c->ev_copy.push_back(e);
         }
         CK(cudaEventRecord(c->ev_copy[sb], c->stream_copy));
-    }
-    rc = run_pipeline(c, n, c->res.in_u8, true, w, true);
+        return AKZ_OK;
+    };
+    rc = run_pipeline(c, n, c->res.in_u8, true, w, upload);
     if (rc != AKZ_OK) return rc;
     return collect_features(c, n, outs);
 }

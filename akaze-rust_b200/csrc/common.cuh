@@ -55,7 +55,9 @@ struct PlanDev {
     int n_orient_windows;
     int grid_shift;        // dedup hash grid: cell = 1<<grid_shift full-resolution pixels
     int grid_w, grid_h;
-    int pool_cap;          // entries per class-parity pool of the cache pass (per image)
+    int pool_cap;          // entries per class-parity pool of the single-warp cache pass (per image)
+    int lgrid_shift;       // level-pipelined cache pass: one hash grid per level in shared memory, cell = 1<<lgrid_shift px
+    int lgrid_w, lgrid_h;
     LevelDev lv[kMaxLevels];
 };
 
@@ -118,7 +120,8 @@ struct Buffers {
     int* c_cls = nullptr;
     int* c_next = nullptr;
     int* grid = nullptr;                // [B][2][grid_cells]
-    unsigned char* dedup_pool = nullptr;  // [B][dedup_pool_bytes()] pools of the shared-memory cache pass
+    unsigned char* dedup_pool = nullptr;  // [B][dedup_pool_bytes()] pools of the single-warp cache pass
+    unsigned char* level_pool = nullptr;  // [B][dedup_level_pool_bytes()] per-level pools of the level-pipelined cache pass
     unsigned int* n_cache = nullptr;    // [B]
     unsigned int* n_cand_total = nullptr;  // [B]
     unsigned int* keep_flag = nullptr;  // [B][kp_cap]
@@ -158,6 +161,7 @@ int launch_compact(const Launch& L, const Plan& P, const Buffers& B);
 // keypoints.cu
 cudaError_t init_keypoint_attributes();
 size_t dedup_pool_bytes(const Plan& P);
+size_t dedup_level_pool_bytes(uint32_t cand_cap);
 int launch_dedup(const Launch& L, const Plan& P, const Buffers& B);
 int launch_finalize(const Launch& L, const Plan& P, const Buffers& B);
 int launch_descriptors(const Launch& L, const Plan& P, const Buffers& B);

@@ -20,6 +20,7 @@ namespace akz {
 namespace {
 
 __device__ __forceinline__ bool image_fits_smem_pass(const PlanDev* plan, const unsigned int* lo);
+__device__ __forceinline__ bool image_fits_level_pass(const PlanDev* plan, const unsigned int* lo);
 
 // ------------------------------------------------------------------------------------------------
 // K5a: greedy cache pass, one warp per image, working set in global memory (fallback for images whose
@@ -29,7 +30,7 @@ __global__ void __launch_bounds__(32)
 k_dedup(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ cand, const unsigned int* __restrict__ level_off,
         const float* __restrict__ ldet_plane, int batch, unsigned int cand_cap, unsigned int kp_cap,
         volatile float* c_x, volatile float* c_y, volatile float* c_resp, volatile int* c_cls, volatile int* c_next,
-        volatile int* grid, unsigned int* __restrict__ n_cache, unsigned int* __restrict__ err_flags) {
+        volatile int* grid, unsigned int* __restrict__ n_cache, unsigned int* __restrict__ err_flags, int fast_pass) {
     const int img = blockIdx.x;
     const int lane = threadIdx.x;
     const unsigned int FULL = 0xffffffffu;
@@ -47,7 +48,8 @@ k_dedup(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ cand,
         if (lane == 0) n_cache[img] = 0;
         return;
     }
-    if (image_fits_smem_pass(plan, lo)) return;  // handled by k_dedup_smem
+    // handled by the fast pass that runs beside this kernel (1 = k_dedup_levels, 0 = k_dedup_smem)
+    if (fast_pass == 1 ? image_fits_level_pass(plan, lo) : image_fits_smem_pass(plan, lo)) return;
     unsigned int n = 0;  // cache length (uniform across lanes)
     bool overflow = false;
 
@@ -392,6 +394,264 @@ k_dedup_smem(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ 
     if (lane == 0) {
         n_cache[img] = n;
         if (overflow) atomicOr(&err_flags[img], (unsigned int)kErrKpOverflow);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5a'': the same greedy pass, one WARP PER LEVEL, pipelined down the image (default).
+//
+// The sequential pass visits the levels one after the other, but a level-L candidate at full-resolution row Y only ever
+// reads or changes cache entries of classes L and L-1 that lie within size_L of it. So level L may run concurrently with
+// level L-1 as long as it stays far enough BEHIND it: when the level L-1 warp works on the candidate at row P, everything
+// it will still touch lies at rows >= P - size_{L-1} - 2 (lookups, replacements) or in hash cells at rows >= P (inserts),
+// and the level-L warp at row Y touches rows <= Y + size_L + 2. With
+//     P >= Y + size_L + size_{L-1} + cell + 3
+// the two never meet (rows AND hash-cell rows are disjoint), hence level L sees exactly the state the sequential pass
+// would show it: every level-(L-1) decision that can influence it has been taken, none of its own writes can influence a
+// pending level-(L-1) decision. Each warp publishes the row of its first undecided candidate (s_progress), its follower
+// spins on it. Within a warp the pass is k_dedup_smem's (eight speculative candidates per step, exact conflict rule).
+//
+// Slots: the sequential pass numbers cache slots in append order = (level, running index inside the level). That pair is
+// the KEY of an entry (a replacement keeps the key of the slot it takes over), "lowest slot first" is "lowest key first",
+// and the final slot numbers are the keys compacted by a prefix sum over the levels' append counts once all warps are
+// through. Entries live in per-level pools (class L = created by warp L: appended or replaced into), each with its own
+// hash grid of u16 heads in shared memory; a level-L candidate searches the grids of L and L-1.
+// 20 k candidates of a 1080p frame: 16 warps take ~1/6 of the time the single warp took.
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned int kDeadKey = 0xffffffffu;
+constexpr int kKeyShift = 20;               // key = (level of the append << 20) | index of the append inside its level
+constexpr unsigned int kMaxLevelCands = 65534;  // pool indices are u16
+
+__device__ __forceinline__ bool image_fits_level_pass(const PlanDev* plan, const unsigned int* lo) {
+    for (int l = 0; l < plan->n_levels; l++)
+        if (lo[l + 1] - lo[l] > kMaxLevelCands) return false;
+    return true;
+}
+
+struct LevelPools {  // per image: entry e of level L sits at index lo[L] + e of every array (cand_cap entries each)
+    float *x, *y, *resp;
+    unsigned int* key;
+    unsigned short* next;
+    __device__ __forceinline__ LevelPools(unsigned char* slab, unsigned int cap) {
+        x = reinterpret_cast<float*>(slab);
+        y = x + cap;
+        resp = y + cap;
+        key = reinterpret_cast<unsigned int*>(resp + cap);
+        next = reinterpret_cast<unsigned short*>(key + cap);
+    }
+};
+constexpr size_t kLevelPoolBytesPerCand = 4 * 4 + 2;
+
+__global__ void __launch_bounds__(1024)
+k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ cand, const unsigned int* __restrict__ level_off,
+               const float* __restrict__ ldet_plane, int batch, unsigned int cand_cap, unsigned int kp_cap, float* __restrict__ c_x,
+               float* __restrict__ c_y, float* __restrict__ c_resp, int* __restrict__ c_cls, unsigned int* __restrict__ n_cache,
+               unsigned int* __restrict__ err_flags, unsigned char* pools) {
+    extern __shared__ unsigned short s_heads[];  // [n_levels][lgrid cells]
+    __shared__ volatile int s_progress[kMaxLevels];
+    __shared__ unsigned int s_appends[kMaxLevels], s_base[kMaxLevels + 1];
+    __shared__ int s_ok;
+    const unsigned int FULL = 0xffffffffu;
+    const int img = blockIdx.x;
+    const int lane = threadIdx.x & 31, L = threadIdx.x >> 5;  // one warp per level
+    const int nl = plan->n_levels;
+    const unsigned int* cl = cand + (size_t)img * cand_cap;
+    const unsigned int* lo = level_off + (size_t)img * (kMaxLevels + 1);
+    const int gw = plan->lgrid_w, gh = plan->lgrid_h, gshift = plan->lgrid_shift;
+    const int gcells = gw * gh;
+    if (threadIdx.x == 0) s_ok = !(err_flags[img] & kErrCandOverflow) && image_fits_level_pass(plan, lo);
+    for (int i = threadIdx.x; i < nl * gcells; i += blockDim.x) s_heads[i] = kNil;
+    if (threadIdx.x < kMaxLevels) {
+        s_progress[threadIdx.x] = -1;
+        s_appends[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    if (!s_ok) {  // candidate overflow: nothing to do; a level beyond the u16 pools: k_dedup takes the image
+        if (threadIdx.x == 0 && (err_flags[img] & kErrCandOverflow)) n_cache[img] = 0;
+        return;
+    }
+    const LevelPools P(pools + (size_t)img * ((size_t)cand_cap * kLevelPoolBytesPerCand), cand_cap);
+    c_x += (size_t)img * kp_cap;
+    c_y += (size_t)img * kp_cap;
+    c_resp += (size_t)img * kp_cap;
+    c_cls += (size_t)img * kp_cap;
+
+    const LevelDev& lv = plan->lv[L];
+    unsigned short* h_cur = s_heads + (size_t)L * gcells;
+    const unsigned short* h_prv = s_heads + (size_t)(L > 0 ? L - 1 : 0) * gcells;
+    const unsigned int beg = lo[L], end = lo[L + 1];
+    const unsigned int pbeg = L > 0 ? lo[L - 1] : 0u;  // pool base of level L-1
+    const float ratio = lv.ratio, size = lv.kp_size, size_sq = lv.size_sq, hr = lv.half_ratio_m1;
+    const int margin = L > 0 ? (int)ceilf(size + plan->lv[L - 1].kp_size) + (1 << gshift) + 3 : 0;
+    const float* ldet = ldet_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
+    unsigned int n_app = 0;  // appends of this level (uniform across the warp)
+    unsigned int cnt = 0;    // pool entries of this level (appends + replacements)
+
+    unsigned int nx_flat = 0;
+    float nx_resp = 0.0f;
+    if (beg + lane < end) {
+        nx_flat = cl[beg + lane];
+        nx_resp = fabsf(ldet[nx_flat]);  // scale_space_extrema.rs:44
+    }
+    constexpr int GL = 32 / kGroups;  // lanes per candidate
+    const int grp = lane / GL, sub = lane % GL;
+    const bool leader = sub == 0;
+    for (unsigned int base = beg; base < end; base += 32) {
+        const unsigned int my_flat = nx_flat;
+        const float my_resp = nx_resp;
+        if (base + 32 + lane < end) {
+            nx_flat = cl[base + 32 + lane];
+            nx_resp = fabsf(ldet[nx_flat]);
+        }
+        const int n_here = min(32u, end - base);
+        int k0 = 0;
+        while (k0 < n_here) {
+            // publish the row of the first undecided candidate; wait until level L-1 is `margin` rows past this step's last
+            {
+                const unsigned int f0 = __shfl_sync(FULL, my_flat, k0);
+                if (lane == 0) s_progress[L] = (int)((float)(f0 / (unsigned int)lv.w) * ratio);
+                if (L > 0) {
+                    const unsigned int fl = __shfl_sync(FULL, my_flat, min(k0 + kGroups - 1, n_here - 1));
+                    const int need = (int)((float)(fl / (unsigned int)lv.w) * ratio) + margin;
+                    while (s_progress[L - 1] < need) __nanosleep(100);
+                    __threadfence_block();
+                }
+            }
+            const int k = k0 + grp;
+            const bool active = k < n_here;
+            const unsigned int flat = __shfl_sync(FULL, my_flat, k & 31);
+            const float resp = __shfl_sync(FULL, my_resp, k & 31);
+            const int px = (int)(flat % (unsigned int)lv.w), py = (int)(flat / (unsigned int)lv.w);
+            const float qx = (float)px * ratio, qy = (float)py * ratio;  // :62-65 compares the level point * ratio
+            unsigned int best = kDeadKey;  // lowest matching key (= lowest slot)
+            unsigned int best_ref = 0;     // (1 if in the pool of level L-1) << 16 | pool index
+            if (active) {
+                const int cx0 = max(0, ((int)floorf(qx - size) - 1) >> gshift);
+                const int cx1 = min(gw - 1, ((int)floorf(qx + size) + 1) >> gshift);
+                const int cy0 = max(0, ((int)floorf(qy - size) - 1) >> gshift);
+                const int cy1 = min(gh - 1, ((int)floorf(qy + size) + 1) >> gshift);
+                const int nx = cx1 - cx0 + 1;
+                const int ncell = nx * (cy1 - cy0 + 1);
+                const int ntot = (L > 0) ? 2 * ncell : ncell;
+                for (int c = sub; c < ntot; c += GL) {
+                    const bool prev = c >= ncell;
+                    const int cc = prev ? c - ncell : c;
+                    const int cell = (cy0 + cc / nx) * gw + (cx0 + cc % nx);
+                    const unsigned int eb = prev ? pbeg : beg;
+                    unsigned short e = prev ? h_prv[cell] : h_cur[cell];
+                    while (e != kNil) {
+                        const unsigned int at = eb + e;
+                        const float dx = qx - P.x[at], dy = qy - P.y[at];
+                        const float dist = dx * dx + dy * dy;
+                        const unsigned int key = P.key[at];  // kDeadKey = replaced entry: never < best
+                        if (dist <= size_sq && key < best) {
+                            best = key;
+                            best_ref = ((prev ? 1u : 0u) << 16) | e;
+                        }
+                        e = P.next[at];
+                    }
+                }
+            }
+#pragma unroll
+            for (int o = 1; o < GL; o <<= 1) {
+                const unsigned int ob = __shfl_xor_sync(FULL, best, o);
+                const unsigned int orf = __shfl_xor_sync(FULL, best_ref, o);
+                if (ob < best) {
+                    best = ob;
+                    best_ref = orf;
+                }
+            }
+            const unsigned int b_at = ((best_ref >> 16) ? pbeg : beg) + (best_ref & 0xffffu);
+            int act = 0;  // 0 = drop, 1 = append, 2 = replace the entry holding key `best`
+            if (active) {
+                if (best == kDeadKey) act = 1;
+                else if (resp > P.resp[b_at]) act = 2;  // :67
+            }
+            const float fx = (float)px * ratio + hr, fy = (float)py * ratio + hr;  // :89-92
+            // conflict rule of k_dedup_smem: an earlier candidate a of this step that writes changes b's decision only if
+            // its new entry lies within `size` of b, or it replaces the very slot b matched
+            bool conflict = false;
+#pragma unroll
+            for (int a = 0; a < kGroups - 1; a++) {
+                const int a_act = __shfl_sync(FULL, act, a * GL);
+                const float a_fx = __shfl_sync(FULL, fx, a * GL), a_fy = __shfl_sync(FULL, fy, a * GL);
+                const unsigned int a_best = __shfl_sync(FULL, best, a * GL);
+                if (a < grp && a_act != 0 && active) {
+                    const float dx = qx - a_fx, dy = qy - a_fy;
+                    const float dist = dx * dx + dy * dy;
+                    if (dist <= size_sq || (a_act == 2 && a_best == best)) conflict = true;
+                }
+            }
+            const unsigned int cmask = __ballot_sync(FULL, conflict && leader);
+            const int n_act = min(kGroups, n_here - k0);
+            const int n_commit = cmask ? min(n_act, (__ffs(cmask) - 1) / GL) : n_act;  // >= 1: group 0 never conflicts
+            const bool commits = leader && grp < n_commit;
+            const unsigned int amask = __ballot_sync(FULL, commits && act == 1);
+            const unsigned int wmask = __ballot_sync(FULL, commits && act != 0);
+            const unsigned int lt = (1u << lane) - 1u;
+            if (commits && act != 0) {
+                const unsigned int key = (act == 1) ? (((unsigned int)L << kKeyShift) | (n_app + __popc(amask & lt))) : best;
+                const unsigned int e = cnt + __popc(wmask & lt);  // < candidates of this level
+                const unsigned int at = beg + e;
+                if (act == 2) P.key[b_at] = kDeadKey;  // the old occupant is dead; it stays on its cell list
+                P.x[at] = fx;
+                P.y[at] = fy;
+                P.resp[at] = resp;
+                P.key[at] = key;
+                const int ncx = min(gw - 1, max(0, (int)fx >> gshift));
+                const int ncy = min(gh - 1, max(0, (int)fy >> gshift));
+                const int ncl = ncy * gw + ncx;
+                // writers that hash to the same cell link in lane order, the others all at once
+                const unsigned int same = __match_any_sync(wmask, ncl);
+                const int rank = __popc(same & lt), nsame = __popc(same);
+                for (int r = 0; r < nsame; r++) {
+                    if (r == rank) {
+                        P.next[at] = h_cur[ncl];
+                        h_cur[ncl] = (unsigned short)e;
+                    }
+                    __syncwarp(same);
+                }
+            }
+            n_app += __popc(amask);
+            cnt += __popc(wmask);
+            k0 += n_commit;
+            __syncwarp();
+            __threadfence_block();  // this step's entries and links are visible before the progress moves on
+        }
+    }
+    __threadfence_block();
+    if (lane == 0) {
+        s_appends[L] = n_app;
+        s_progress[L] = 0x7fffffff;  // level finished
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int acc = 0;
+        for (int l = 0; l < nl; l++) {
+            s_base[l] = acc;
+            acc += s_appends[l];
+        }
+        s_base[nl] = acc;
+        if (acc > kp_cap) {
+            atomicOr(&err_flags[img], (unsigned int)kErrKpOverflow);
+            n_cache[img] = 0;
+        } else {
+            n_cache[img] = acc;
+        }
+    }
+    __syncthreads();
+    if (s_base[nl] > kp_cap) return;
+    // every live entry goes to its final slot: base of the level that appended it + its index there
+    for (unsigned int e = lane; e < cnt; e += 32) {
+        const unsigned int at = beg + e;
+        const unsigned int key = P.key[at];
+        if (key != kDeadKey) {
+            const unsigned int slot = s_base[key >> kKeyShift] + (key & ((1u << kKeyShift) - 1u));
+            c_x[slot] = P.x[at];
+            c_y[slot] = P.y[at];
+            c_resp[slot] = P.resp[at];
+            c_cls[slot] = L;
+        }
     }
 }
 
@@ -826,20 +1086,35 @@ k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plan
 
 cudaError_t init_keypoint_attributes() {
     // see init_detector_attributes: the cache pass must not pin a small shared-memory carveout on the SMs it lives on
+    cudaError_t e = cudaFuncSetAttribute(k_dedup_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
     if (getenv("AKZ_NO_CARVEOUT") != nullptr) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(k_dedup_smem, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(k_dedup_levels, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_dedup_smem, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_dedup, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 size_t dedup_pool_bytes(const Plan& P) { return (size_t)P.dev.pool_cap * kPoolBytesPerEntry; }
+size_t dedup_level_pool_bytes(uint32_t cand_cap) { return (size_t)cand_cap * kLevelPoolBytesPerCand; }
+static size_t level_pass_smem(const Plan& P) { return (size_t)P.dev.n_levels * P.dev.lgrid_w * P.dev.lgrid_h * sizeof(unsigned short); }
 
 int launch_dedup(const Launch& L, const Plan& P, const Buffers& B) {
-    // every image is handled by exactly one of the two kernels (image_fits_smem_pass)
-    k_dedup_smem<<<L.batch, 32, 0, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap, L.kp_cap, B.c_x,
-                                               B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags, B.dedup_pool);
+    // every image is handled by exactly one of the two kernels launched here (image_fits_*_pass)
+    static const bool single_warp = getenv("AKZ_DEDUP_SINGLE") != nullptr;  // A/B switch: the one-warp-per-image pass
+    const size_t smem = level_pass_smem(P);
+    const bool levels = !single_warp && smem <= 200 * 1024;
+    if (levels) {
+        k_dedup_levels<<<L.batch, 32 * P.dev.n_levels, smem, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap,
+                                                                        L.kp_cap, B.c_x, B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags,
+                                                                        B.level_pool);
+    } else {
+        k_dedup_smem<<<L.batch, 32, 0, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap, L.kp_cap, B.c_x,
+                                                   B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags, B.dedup_pool);
+    }
     k_dedup<<<L.batch, 32, 0, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap, L.kp_cap,
-                                           B.c_x, B.c_y, B.c_resp, B.c_cls, B.c_next, B.grid, B.n_cache, B.err_flags);
+                                           B.c_x, B.c_y, B.c_resp, B.c_cls, B.c_next, B.grid, B.n_cache, B.err_flags, levels ? 1 : 0);
     return 2;
 }
 

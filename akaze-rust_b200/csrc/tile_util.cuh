@@ -73,6 +73,22 @@ __device__ __forceinline__ void tap3x4(float k0, float k1, float k2, const float
     }
 }
 
+// out[j] = (((k0 * a[j] + k1 * b[j]) + k2 * c[j]) + k3 * d[j]) + k4 * e[j], the 5-tap form of tap3x4
+__device__ __forceinline__ void tap5x4(float k0, float k1, float k2, float k3, float k4, const float (&a)[4], const float (&b)[4],
+                                       const float (&c)[4], const float (&d)[4], const float (&e)[4], float (&out)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; j += 2) {
+        float pa0, pa1, pb0, pb1, pc0, pc1, pd0, pd1, pe0, pe1;
+        mul2(a[j], a[j + 1], k0, pa0, pa1);
+        mul2(b[j], b[j + 1], k1, pb0, pb1);
+        mul2(c[j], c[j + 1], k2, pc0, pc1);
+        mul2(d[j], d[j + 1], k3, pd0, pd1);
+        mul2(e[j], e[j + 1], k4, pe0, pe1);
+        out[j] = (((pa0 + pb0) + pc0) + pd0) + pe0;
+        out[j + 1] = (((pa1 + pb1) + pc1) + pd1) + pe1;
+    }
+}
+
 // v[0..11] = row[cx-4 .. cx+7] (cx a multiple of 4)
 __device__ __forceinline__ void load12(const float* row, int cx, float (&v)[12]) {
     const float4 a = ld4(row + cx - 4), b = ld4(row + cx), c = ld4(row + cx + 4);

@@ -348,6 +348,7 @@ def run_extract(args, images, h, w, n_img, full):
     reps = (n_img + uniq - 1) // uniq
     h_imgs = torch.empty((n_img, h, w), dtype=torch.uint8, pin_memory=True)
     h_imgs.copy_(h_uniq.repeat(reps, 1, 1)[:n_img])
+    h_np = h_imgs.numpy()
     d_imgs = h_imgs.to(dev)
     torch.cuda.synchronize()
     eng = A.Engine(local, w, h, B)
@@ -370,7 +371,7 @@ def run_extract(args, images, h, w, n_img, full):
         kp, d2h, kept = 0, 0, []
         for i0 in range(0, n_img, B):
             m = min(B, n_img - i0)
-            fs = eng.extract_batch_u8([h_imgs[i0 + j].numpy() for j in range(m)], cfg)
+            fs = eng.extract_batch_u8(h_np[i0:i0 + m], cfg)  # (m, h, w) view of the pinned host images
             for j, f in enumerate(fs):  # keypoints + descriptors are in (pinned) host memory now; only the counts are read here
                 kp += f.count
                 d2h += f.count * (28 + 64)
@@ -489,7 +490,7 @@ def run_extract(args, images, h, w, n_img, full):
         out["parity_check"]["what"] = ("keypoints + descriptors of images 0..%d of the LAST timed e2e step (batch of %d, default mode) vs the CPU oracle on the "
                                        "same images" % (n_par - 1, n_img))
     eng.close()
-    del d_imgs, h_imgs
+    del d_imgs, h_np, h_imgs
     torch.cuda.empty_cache()
     return out
 

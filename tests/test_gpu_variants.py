@@ -25,8 +25,10 @@ import numpy as np
 import akaze_rust_b200 as A
 import np_restatement as R
 imgs = [R.synthetic_image(h, w, seed=s) for (h, w, s) in ((480, 640, 1), (480, 640, 2), (272, 360, 3), (272, 360, 4))]
+# dense noise: > 4096 candidates on one level (the single-warp cache pass hands the image to its global-memory fallback)
+imgs.append(np.random.default_rng(5).integers(0, 256, (600, 800), dtype=np.uint8))
 out = {{}}
-for shape in ((480, 640), (272, 360)):
+for shape in ((480, 640), (272, 360), (600, 800)):
     batch = [im for im in imgs if im.shape == shape]
     eng = A.Engine(0, shape[1], shape[0], len(batch))
     fs = eng.extract_batch_u8(batch)
@@ -53,7 +55,7 @@ def test_kernel_variants_agree(akz):
     base = run_variant({})
     assert all(n > 100 for _h, n in base.values()), base
     for env in ({"AKZ_DET_SMEM": "1"}, {"AKZ_FED_OLD": "1"}, {"AKZ_NO_CONTRAST_FUSION": "1"}, {"AKZ_DETECTOR_TILE": "1"},
-                {"AKZ_FED_MAXT": "8"}, {"AKZ_SERIAL_LANES": "1"}):
+                {"AKZ_FED_MAXT": "8"}, {"AKZ_SERIAL_LANES": "1"}, {"AKZ_DEDUP_SINGLE": "1"}, {"AKZ_NO_RAMP": "1"}):
         assert run_variant(env) == base, env
 
 
