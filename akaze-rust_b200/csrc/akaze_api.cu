@@ -484,6 +484,7 @@ static int ensure_lane(akz_context* c, Lane& ln, int batch) {
     CK(dalloc(A, &B.level_pool, nb * dedup_level_pool_bytes(c->cand_cap)));
     CK(dalloc(A, &B.keep_flag, kc));
     CK(dalloc(A, &B.cls_range, nb * kMaxLevels * 2));
+    CK(dalloc(A, &B.upper_done, nb));
     CK(dalloc(A, &B.plan_dev, 1));
     CK(cudaMemcpy(B.plan_dev, &P.dev, sizeof(PlanDev), cudaMemcpyHostToDevice));
     if (!ln.ev_stencil) {
@@ -541,11 +542,19 @@ static void make_schedule(akz_context* c, uint32_t n, bool host_io) {
     c->sched.clear();
     const uint32_t m = sub_batch_of(c, n);
     static const bool no_ramp = getenv("AKZ_NO_RAMP") != nullptr;  // A/B switch
-    if (!host_io || no_ramp || (c->flags & AKZ_KEEP_EVOLUTIONS) || n < 8) {
+    // a sub-batch must keep the stencil stream busy for as long as the cache pass of its predecessor runs (the pass is
+    // latency-bound: about as long for 8 images as for 256), which takes ~16 images at any size
+    constexpr uint32_t kMinSub = 16;
+    if (!host_io || no_ramp || (c->flags & AKZ_KEEP_EVOLUTIONS) || n < 2 * kMinSub) {
         for (uint32_t i0 = 0; i0 < n; i0 += m) c->sched.push_back({i0, std::min(m, n - i0)});
         return;
     }
-    const uint32_t tail = std::max<uint32_t>(1u, std::min<uint32_t>(m / 4, n / 8));
+    if (n < 4 * kMinSub) {  // two halves: the second upload and the first download overlap the kernels
+        const uint32_t h = std::min(m, (n + 1) / 2);
+        for (uint32_t i0 = 0; i0 < n; i0 += h) c->sched.push_back({i0, std::min(h, n - i0)});
+        return;
+    }
+    const uint32_t tail = std::max<uint32_t>(kMinSub, std::min<uint32_t>(m / 4, n / 8));
     uint32_t i0 = 0, step = tail;
     while (i0 < n - tail) {
         const uint32_t cnt = std::min(step, n - tail - i0);

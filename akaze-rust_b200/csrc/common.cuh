@@ -126,6 +126,7 @@ struct Buffers {
     unsigned int* n_cand_total = nullptr;  // [B]
     unsigned int* keep_flag = nullptr;  // [B][kp_cap]
     unsigned int* cls_range = nullptr;  // [B][kMaxLevels][2] slot range per class_id
+    unsigned int* upper_done = nullptr; // [B] 1: the cache pass already ran the upper-scale filter (verdicts in keep_flag)
     unsigned int* n_kp = nullptr;       // [B]
     unsigned int* err_flags = nullptr;  // [B]
     akz_keypoint* kps = nullptr;        // [B][kp_cap]

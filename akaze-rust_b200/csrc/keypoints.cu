@@ -30,7 +30,8 @@ __global__ void __launch_bounds__(32)
 k_dedup(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ cand, const unsigned int* __restrict__ level_off,
         const float* __restrict__ ldet_plane, int batch, unsigned int cand_cap, unsigned int kp_cap,
         volatile float* c_x, volatile float* c_y, volatile float* c_resp, volatile int* c_cls, volatile int* c_next,
-        volatile int* grid, unsigned int* __restrict__ n_cache, unsigned int* __restrict__ err_flags, int fast_pass) {
+        volatile int* grid, unsigned int* __restrict__ n_cache, unsigned int* __restrict__ err_flags, int fast_pass,
+        unsigned int* __restrict__ upper_done) {
     const int img = blockIdx.x;
     const int lane = threadIdx.x;
     const unsigned int FULL = 0xffffffffu;
@@ -50,6 +51,7 @@ k_dedup(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ cand,
     }
     // handled by the fast pass that runs beside this kernel (1 = k_dedup_levels, 0 = k_dedup_smem)
     if (fast_pass == 1 ? image_fits_level_pass(plan, lo) : image_fits_smem_pass(plan, lo)) return;
+    if (lane == 0) upper_done[img] = 0;  // k_filter_refine runs the upper-scale scan for this image
     unsigned int n = 0;  // cache length (uniform across lanes)
     bool overflow = false;
 
@@ -213,7 +215,7 @@ __global__ void __launch_bounds__(32)
 k_dedup_smem(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ cand, const unsigned int* __restrict__ level_off,
              const float* __restrict__ ldet_plane, int batch, unsigned int cand_cap, unsigned int kp_cap, float* __restrict__ c_x,
              float* __restrict__ c_y, float* __restrict__ c_resp, int* __restrict__ c_cls, unsigned int* __restrict__ n_cache,
-             unsigned int* __restrict__ err_flags, unsigned char* pools) {
+             unsigned int* __restrict__ err_flags, unsigned char* pools, unsigned int* __restrict__ upper_done) {
     __shared__ DedupSmem S;
     const int img = blockIdx.x;
     const DedupPool G(pools + (size_t)img * ((size_t)plan->pool_cap * kPoolBytesPerEntry), plan->pool_cap);
@@ -226,6 +228,7 @@ k_dedup_smem(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ 
         return;
     }
     if (!image_fits_smem_pass(plan, lo)) return;  // handled by k_dedup
+    if (lane == 0) upper_done[img] = 0;
     const int gw = plan->grid_w, gh = plan->grid_h, gshift = plan->grid_shift;
     const int gcells = gw * gh;
     c_x += (size_t)img * kp_cap;
@@ -442,11 +445,13 @@ struct LevelPools {  // per image: entry e of level L sits at index lo[L] + e of
 };
 constexpr size_t kLevelPoolBytesPerCand = 4 * 4 + 2;
 
+template <int KG>  // candidates decided per step (32 / KG lanes each)
 __global__ void __launch_bounds__(1024)
 k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ cand, const unsigned int* __restrict__ level_off,
                const float* __restrict__ ldet_plane, int batch, unsigned int cand_cap, unsigned int kp_cap, float* __restrict__ c_x,
                float* __restrict__ c_y, float* __restrict__ c_resp, int* __restrict__ c_cls, unsigned int* __restrict__ n_cache,
-               unsigned int* __restrict__ err_flags, unsigned char* pools) {
+               unsigned int* __restrict__ err_flags, unsigned char* pools, unsigned int* __restrict__ keep_flag,
+               unsigned int* __restrict__ upper_done) {
     extern __shared__ unsigned short s_heads[];  // [n_levels][lgrid cells]
     __shared__ volatile int s_progress[kMaxLevels];
     __shared__ unsigned int s_appends[kMaxLevels], s_base[kMaxLevels + 1];
@@ -467,7 +472,10 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
     }
     __syncthreads();
     if (!s_ok) {  // candidate overflow: nothing to do; a level beyond the u16 pools: k_dedup takes the image
-        if (threadIdx.x == 0 && (err_flags[img] & kErrCandOverflow)) n_cache[img] = 0;
+        if (threadIdx.x == 0 && (err_flags[img] & kErrCandOverflow)) {
+            n_cache[img] = 0;
+            upper_done[img] = 0;
+        }
         return;
     }
     const LevelPools P(pools + (size_t)img * ((size_t)cand_cap * kLevelPoolBytesPerCand), cand_cap);
@@ -493,7 +501,7 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
         nx_flat = cl[beg + lane];
         nx_resp = fabsf(ldet[nx_flat]);  // scale_space_extrema.rs:44
     }
-    constexpr int GL = 32 / kGroups;  // lanes per candidate
+    constexpr int GL = 32 / KG;  // lanes per candidate
     const int grp = lane / GL, sub = lane % GL;
     const bool leader = sub == 0;
     for (unsigned int base = beg; base < end; base += 32) {
@@ -511,7 +519,7 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
                 const unsigned int f0 = __shfl_sync(FULL, my_flat, k0);
                 if (lane == 0) s_progress[L] = (int)((float)(f0 / (unsigned int)lv.w) * ratio);
                 if (L > 0) {
-                    const unsigned int fl = __shfl_sync(FULL, my_flat, min(k0 + kGroups - 1, n_here - 1));
+                    const unsigned int fl = __shfl_sync(FULL, my_flat, min(k0 + KG - 1, n_here - 1));
                     const int need = (int)((float)(fl / (unsigned int)lv.w) * ratio) + margin;
                     while (s_progress[L - 1] < need) __nanosleep(100);
                     __threadfence_block();
@@ -572,7 +580,7 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
             // its new entry lies within `size` of b, or it replaces the very slot b matched
             bool conflict = false;
 #pragma unroll
-            for (int a = 0; a < kGroups - 1; a++) {
+            for (int a = 0; a < KG - 1; a++) {
                 const int a_act = __shfl_sync(FULL, act, a * GL);
                 const float a_fx = __shfl_sync(FULL, fx, a * GL), a_fy = __shfl_sync(FULL, fy, a * GL);
                 const unsigned int a_best = __shfl_sync(FULL, best, a * GL);
@@ -583,7 +591,7 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
                 }
             }
             const unsigned int cmask = __ballot_sync(FULL, conflict && leader);
-            const int n_act = min(kGroups, n_here - k0);
+            const int n_act = min(KG, n_here - k0);
             const int n_commit = cmask ? min(n_act, (__ffs(cmask) - 1) / GL) : n_act;  // >= 1: group 0 never conflicts
             const bool commits = leader && grp < n_commit;
             const unsigned int amask = __ballot_sync(FULL, commits && act == 1);
@@ -638,20 +646,53 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
         } else {
             n_cache[img] = acc;
         }
+        upper_done[img] = 1;  // the upper-scale filter below replaces k_filter_refine's scan for this image
     }
     __syncthreads();
     if (s_base[nl] > kp_cap) return;
-    // every live entry goes to its final slot: base of the level that appended it + its index there
+    // Every live entry goes to its final slot: base of the level that appended it + its index there. The upper-scale filter
+    // (scale_space_extrema.rs:111-129) rides along: entry i is dropped if a class i+1 entry in a slot >= i lies within size_i
+    // of it -- the class L+1 entries are exactly the live entries of pool L+1, and their hash grid is still in shared memory,
+    // so the scan over the whole class (quadratic in the keypoint count; 13 x the time for 4.8 x the keypoints at 3840x2160)
+    // becomes a look into at most a handful of cells.
+    keep_flag += (size_t)img * kp_cap;
+    const bool has_up = L + 1 < nl;
+    const unsigned short* h_up = s_heads + (size_t)(has_up ? L + 1 : L) * gcells;
+    const unsigned int ubeg = lo[has_up ? L + 1 : L];
+    constexpr unsigned int kIdxMask = (1u << kKeyShift) - 1u;
     for (unsigned int e = lane; e < cnt; e += 32) {
         const unsigned int at = beg + e;
         const unsigned int key = P.key[at];
-        if (key != kDeadKey) {
-            const unsigned int slot = s_base[key >> kKeyShift] + (key & ((1u << kKeyShift) - 1u));
-            c_x[slot] = P.x[at];
-            c_y[slot] = P.y[at];
-            c_resp[slot] = P.resp[at];
-            c_cls[slot] = L;
+        if (key == kDeadKey) continue;
+        const unsigned int slot = s_base[key >> kKeyShift] + (key & kIdxMask);
+        const float xi = P.x[at], yi = P.y[at];
+        bool repeated = false;
+        if (has_up) {
+            const int cx0 = max(0, ((int)floorf(xi - size) - 1) >> gshift), cx1 = min(gw - 1, ((int)floorf(xi + size) + 1) >> gshift);
+            const int cy0 = max(0, ((int)floorf(yi - size) - 1) >> gshift), cy1 = min(gh - 1, ((int)floorf(yi + size) + 1) >> gshift);
+            for (int cy = cy0; cy <= cy1 && !repeated; cy++)
+                for (int cx = cx0; cx <= cx1 && !repeated; cx++) {
+                    unsigned short u = h_up[cy * gw + cx];
+                    while (u != kNil) {
+                        const unsigned int ua = ubeg + u;
+                        const unsigned int ukey = P.key[ua];
+                        if (ukey != kDeadKey && s_base[ukey >> kKeyShift] + (ukey & kIdxMask) >= slot) {  // :115 scans slots j >= i
+                            const float dx = xi - P.x[ua], dy = yi - P.y[ua];
+                            const float dist = dx * dx + dy * dy;
+                            if (dist <= size_sq) {
+                                repeated = true;
+                                break;
+                            }
+                        }
+                        u = P.next[ua];
+                    }
+                }
         }
+        c_x[slot] = xi;
+        c_y[slot] = yi;
+        c_resp[slot] = P.resp[at];
+        c_cls[slot] = L;
+        keep_flag[slot] = repeated ? 0u : 1u;
     }
 }
 
@@ -688,21 +729,22 @@ __global__ void k_filter_refine(const PlanDev* __restrict__ plan, const float* _
                                 unsigned int kp_cap, const float* __restrict__ c_x, const float* __restrict__ c_y,
                                 const int* __restrict__ c_cls, const unsigned int* __restrict__ n_cache,
                                 const unsigned int* __restrict__ cls_range, float* __restrict__ r_x, float* __restrict__ r_y,
-                                unsigned int* __restrict__ keep_flag) {
+                                unsigned int* __restrict__ keep_flag, const unsigned int* __restrict__ upper_done) {
     const int img = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const unsigned int n = n_cache[img];
     const size_t o = (size_t)img * kp_cap;
+    const bool scanned = upper_done[img] != 0;  // k_dedup_levels already ran the upper-scale filter: keep_flag[i] holds its verdict
     const int warps = (blockDim.x >> 5) * gridDim.x;
     for (unsigned int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); i < n; i += warps) {
         const int cls = c_cls[o + i];
         const LevelDev& lv = plan->lv[cls];
         const float xi = c_x[o + i], yi = c_y[o + i];
         const float size_sq = lv.size_sq;
-        bool rep = false;
+        bool rep = scanned && keep_flag[o + i] == 0u;
         // :115 scans slots j >= i for class_id + 1; those all lie inside that class's slot range
         unsigned int jb = i, je = 0;
-        if (cls + 1 < plan->n_levels) {
+        if (!scanned && cls + 1 < plan->n_levels) {
             const unsigned int rl = cls_range[((size_t)img * kMaxLevels + cls + 1) * 2 + 0];
             const unsigned int rh = cls_range[((size_t)img * kMaxLevels + cls + 1) * 2 + 1];
             if (rl != 0xffffffffu) {
@@ -1086,10 +1128,14 @@ k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plan
 
 cudaError_t init_keypoint_attributes() {
     // see init_detector_attributes: the cache pass must not pin a small shared-memory carveout on the SMs it lives on
-    cudaError_t e = cudaFuncSetAttribute(k_dedup_levels, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_dedup_levels<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_dedup_levels<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
     if (getenv("AKZ_NO_CARVEOUT") != nullptr) return cudaSuccess;
-    e = cudaFuncSetAttribute(k_dedup_levels, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    e = cudaFuncSetAttribute(k_dedup_levels<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_dedup_levels<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_dedup_smem, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
@@ -1105,16 +1151,21 @@ int launch_dedup(const Launch& L, const Plan& P, const Buffers& B) {
     static const bool single_warp = getenv("AKZ_DEDUP_SINGLE") != nullptr;  // A/B switch: the one-warp-per-image pass
     const size_t smem = level_pass_smem(P);
     const bool levels = !single_warp && smem <= 200 * 1024;
-    if (levels) {
-        k_dedup_levels<<<L.batch, 32 * P.dev.n_levels, smem, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap,
-                                                                        L.kp_cap, B.c_x, B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags,
-                                                                        B.level_pool);
+    static const int groups = getenv("AKZ_DEDUP_GROUPS") ? atoi(getenv("AKZ_DEDUP_GROUPS")) : 8;  // A/B switch
+    if (levels && groups == 16) {
+        k_dedup_levels<16><<<L.batch, 32 * P.dev.n_levels, smem, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap,
+                                                                            L.kp_cap, B.c_x, B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags,
+                                                                            B.level_pool, B.keep_flag, B.upper_done);
+    } else if (levels) {
+        k_dedup_levels<8><<<L.batch, 32 * P.dev.n_levels, smem, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap,
+                                                                           L.kp_cap, B.c_x, B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags,
+                                                                           B.level_pool, B.keep_flag, B.upper_done);
     } else {
         k_dedup_smem<<<L.batch, 32, 0, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap, L.kp_cap, B.c_x,
-                                                   B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags, B.dedup_pool);
+                                                   B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags, B.dedup_pool, B.upper_done);
     }
     k_dedup<<<L.batch, 32, 0, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap, L.kp_cap,
-                                           B.c_x, B.c_y, B.c_resp, B.c_cls, B.c_next, B.grid, B.n_cache, B.err_flags, levels ? 1 : 0);
+                                           B.c_x, B.c_y, B.c_resp, B.c_cls, B.c_next, B.grid, B.n_cache, B.err_flags, levels ? 1 : 0, B.upper_done);
     return 2;
 }
 
@@ -1124,7 +1175,7 @@ int launch_finalize(const Launch& L, const Plan& P, const Buffers& B) {
     dim3 g1(64, L.batch);
     k_class_ranges<<<L.batch, 256, 0, L.stream>>>(B.c_cls, B.n_cache, L.kp_cap, B.cls_range);
     k_filter_refine<<<g1, 256, 0, L.stream>>>(B.plan_dev, B.Ldet, L.batch, L.kp_cap, B.c_x, B.c_y, B.c_cls, B.n_cache, B.cls_range,
-                                              r_x, r_y, B.keep_flag);
+                                              r_x, r_y, B.keep_flag, B.upper_done);
     k_keep_scan<<<L.batch, 1024, 0, L.stream>>>(B.keep_flag, B.n_cache, B.n_kp, L.kp_cap);
     dim3 g3(16, L.batch);
     k_orientation<<<g3, 128, 0, L.stream>>>(B.plan_dev, B.Lx, B.Ly, L.batch, L.kp_cap, r_x, r_y, B.c_resp, B.c_cls, B.keep_flag,

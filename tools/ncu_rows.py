@@ -9,7 +9,11 @@ SEL = [("gpu__time_duration.sum", "ms"), ("smsp__issue_active.avg.pct_of_peak_su
        ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "lsu_wf%"),
        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram%"), ("dram__bytes_read.sum", "rdMB"), ("dram__bytes_write.sum", "wrMB"),
        ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "fma%"), ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu%"),
-       ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%"), ("smsp__inst_executed.sum", "Minst"),
+       ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "lsu%"),
+       ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64%"), ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "xu%"),
+       ("sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active", "fmaH%"), ("sm__pipe_fmalite_cycles_active.avg.pct_of_peak_sustained_active", "fmaL%"),
+       ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor%"),
+       ("sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active", "tensI%"), ("smsp__inst_executed.sum", "Minst"),
        ("launch__registers_per_thread", "regs"), ("launch__occupancy_limit_shared_mem", "occ_smem"), ("launch__occupancy_limit_registers", "occ_reg")]
 STALL = "smsp__average_warps_issue_stalled_%s_per_issue_active.ratio"
 REASONS = ["long_scoreboard", "short_scoreboard", "mio_throttle", "lg_throttle", "wait", "math_pipe_throttle", "not_selected", "no_instruction",
