@@ -293,6 +293,8 @@ struct Lane {
     cudaEvent_t ev_stencil = nullptr;  // stage A of the sub-batch using this lane has finished
     cudaEvent_t ev_dedup = nullptr;    // the cache pass of the sub-batch using this lane has finished
     cudaEvent_t ev_done = nullptr;     // stage B of the sub-batch using this lane has finished
+    cudaEvent_t ev_prep[kMaxLevels] = {nullptr};  // Lsmooth_l (and for level 1 the consumers of the stored gradients) ready
+    cudaEvent_t ev_det[kMaxLevels] = {nullptr};   // detector(l) has finished
     bool busy = false;
 };
 
@@ -342,6 +344,7 @@ struct akz_context {
     bool sub_batch_auto = true;        // chosen from the free device memory when the plan changes (see prepare)
     cudaStream_t stream = nullptr;     // stage A, copies, and the stream callers may time on
     cudaStream_t stream_kp = nullptr;  // stage B
+    cudaStream_t stream_det = nullptr; // the detectors: detector(l) only needs Lsmooth_l, so it runs beside FED(l) / prep(l+1)
     cudaStream_t stream_copy = nullptr;  // host -> device staging of the inputs, one event per sub-batch
     cudaStream_t stream_d2h = nullptr;   // device -> host copies of the results, sub-batch by sub-batch
     std::vector<cudaEvent_t> ev_copy;
@@ -453,6 +456,7 @@ static int ensure_lane(akz_context* c, Lane& ln, int batch) {
     CK(dalloc(A, &B.Ly, plane));
     CK(dalloc(A, &B.Ldet, plane));
     CK(dalloc(A, &B.Lsmooth, B.keep ? plane : n0));
+    if (!B.keep) CK(dalloc(A, &B.Lsmooth2, n0));
     CK(dalloc(A, &B.Lflow, B.keep ? plane : n0));
     CK(dalloc(A, &B.Ltmp, n0));
     if (B.keep) {
@@ -491,6 +495,10 @@ static int ensure_lane(akz_context* c, Lane& ln, int batch) {
         CK(cudaEventCreateWithFlags(&ln.ev_stencil, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ln.ev_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ln.ev_dedup, cudaEventDisableTiming));
+        for (int l = 0; l < kMaxLevels; l++) {
+            CK(cudaEventCreateWithFlags(&ln.ev_prep[l], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ln.ev_det[l], cudaEventDisableTiming));
+        }
     }
     ln.alloc_batch = batch;
     return AKZ_OK;
@@ -609,7 +617,7 @@ static int prepare(akz_context* c, uint32_t n, uint32_t w, uint32_t h, const akz
             size_t free_b = 0, total_b = 0;
             CK(cudaMemGetInfo(&free_b, &total_b));
             const size_t n0 = (size_t)w * h;
-            const size_t per_image = 4 * (4 * (size_t)np.dev.plane_px + 3 * n0) + 4 * (size_t)np.dev.mask_words + 4 * (size_t)c->cand_cap +
+            const size_t per_image = 4 * (4 * (size_t)np.dev.plane_px + 4 * n0) + 4 * (size_t)np.dev.mask_words + 4 * (size_t)c->cand_cap +
                                      40 * (size_t)c->kp_cap + dedup_pool_bytes(np) + dedup_level_pool_bytes(c->cand_cap) + (1 << 16);
             const size_t fit = (free_b / 2) / (2 * per_image);
             c->sub_batch = (uint32_t)std::max<size_t>(16, std::min<size_t>(256, fit));
@@ -749,14 +757,36 @@ static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8
         Launch LA{c->stream, (int)cnt, c->cand_cap, c->kp_cap};
         CK(cudaMemsetAsync(B.mask, 0, (size_t)P.dev.mask_words * cnt * sizeof(unsigned int), c->stream));
         CK(cudaMemsetAsync(B.err_flags, 0, cnt * sizeof(unsigned int), c->stream));
+        // The detectors run on their own stream: detector(l) reads Lsmooth_l only, so it overlaps FED(l) and prep(l+1) and
+        // fills the SMs the other kernel's last wave leaves idle (every streaming kernel takes a whole register file per
+        // SM, so they only ever meet in those tails; the small octaves are one to two waves long). Lsmooth alternates
+        // between two scratch planes, prep(l) waits for detector(l-2). Level 1's detector overwrites the Lx/Ly planes
+        // that hold the contrast pass's gradients, so it waits for their consumers (FED(1)). Timing mode keeps one stream.
+        static const bool det_inline = getenv("AKZ_DET_INLINE") != nullptr;  // A/B switch: detectors on the main stream
+        const bool split = !c->timing && !det_inline && !B.keep;
+        cudaStream_t sd = split ? c->stream_det : c->stream;
+        Launch LD{sd, (int)cnt, c->cand_cap, c->kp_cap};
         STAGE(AKZ_STAGE_LEVEL0, c->stream, launch_level0(LA, P, B, in, is_u8, in_stride));
-        STAGE(AKZ_STAGE_CONTRAST, c->stream, launch_contrast(LA, P, B));
-        STAGE(AKZ_STAGE_DETECTOR, c->stream, launch_detector(LA, P, B, 0));
-        for (int l = 1; l < P.dev.n_levels; l++) {
-            STAGE(AKZ_STAGE_PREP, c->stream, launch_prep(LA, P, B, l));
-            STAGE(AKZ_STAGE_FED, c->stream, launch_fed(LA, P, B, l));
-            STAGE(AKZ_STAGE_DETECTOR, c->stream, launch_detector(LA, P, B, l));
+        if (split) {
+            CK(cudaEventRecord(ln.ev_prep[0], c->stream));
+            CK(cudaStreamWaitEvent(sd, ln.ev_prep[0], 0));
         }
+        STAGE(AKZ_STAGE_CONTRAST, c->stream, launch_contrast(LA, P, B));
+        STAGE(AKZ_STAGE_DETECTOR, sd, launch_detector(LD, P, B, 0));
+        if (split) CK(cudaEventRecord(ln.ev_det[0], sd));
+        for (int l = 1; l < P.dev.n_levels; l++) {
+            if (split && l >= 2) CK(cudaStreamWaitEvent(c->stream, ln.ev_det[l - 2], 0));  // its Lsmooth scratch plane is free again
+            STAGE(AKZ_STAGE_PREP, c->stream, launch_prep(LA, P, B, l));
+            if (split && l >= 2) CK(cudaEventRecord(ln.ev_prep[l], c->stream));
+            STAGE(AKZ_STAGE_FED, c->stream, launch_fed(LA, P, B, l));
+            if (split) {
+                if (l == 1) CK(cudaEventRecord(ln.ev_prep[l], c->stream));
+                CK(cudaStreamWaitEvent(sd, ln.ev_prep[l], 0));
+            }
+            STAGE(AKZ_STAGE_DETECTOR, sd, launch_detector(LD, P, B, l));
+            if (split) CK(cudaEventRecord(ln.ev_det[l], sd));
+        }
+        if (split) CK(cudaStreamWaitEvent(c->stream, ln.ev_det[P.dev.n_levels - 1], 0));
         STAGE(AKZ_STAGE_COMPACT, c->stream, launch_compact(LA, P, B));
         CK(cudaEventRecord(ln.ev_stencil, c->stream));
         // Order on the main stream: S(0) S(1) F(0) S(2) F(1) ... ; the cache pass D(i) starts on the side stream once
@@ -975,6 +1005,7 @@ int akz_create(int device, uint32_t max_width, uint32_t max_height, uint32_t max
     }
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->stream_kp, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->stream_det, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->stream_d2h, cudaStreamNonBlocking));
     CK(init_detector_attributes());
@@ -1007,8 +1038,14 @@ void akz_destroy(akz_context* c) {
         if (c->lane[l].ev_stencil) cudaEventDestroy(c->lane[l].ev_stencil);
         if (c->lane[l].ev_done) cudaEventDestroy(c->lane[l].ev_done);
         if (c->lane[l].ev_dedup) cudaEventDestroy(c->lane[l].ev_dedup);
+        for (int i = 0; i < kMaxLevels; i++) {
+            if (c->lane[l].ev_prep[i]) cudaEventDestroy(c->lane[l].ev_prep[i]);
+            if (c->lane[l].ev_det[i]) cudaEventDestroy(c->lane[l].ev_det[i]);
+        }
     }
     cudaStreamDestroy(c->stream_kp);
+    cudaStreamSynchronize(c->stream_det);
+    cudaStreamDestroy(c->stream_det);
     for (cudaEvent_t e : c->ev_copy) cudaEventDestroy(e);
     for (cudaEvent_t e : c->ev_stats) cudaEventDestroy(e);
     cudaStreamDestroy(c->stream_copy);
@@ -1204,7 +1241,7 @@ int akz_features_evolution_download(const akz_features* f, uint32_t level, int k
     const float* plane = nullptr;
     switch (kind) {
         case AKZ_LT: plane = B.Lt; break;
-        case AKZ_LSMOOTH: plane = (level == 0) ? B.Lt : B.Lsmooth; break;  // lib.rs:58
+        case AKZ_LSMOOTH: plane = (level == 0) ? B.Lt : B.Lsmooth; break;  // lib.rs:58 (levels >= 1: keep mode only, checked above)
         case AKZ_LX: plane = B.Lx; break;
         case AKZ_LY: plane = B.Ly; break;
         case AKZ_LXX: plane = B.Lxx; break;

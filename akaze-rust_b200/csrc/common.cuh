@@ -90,6 +90,8 @@ struct Buffers {
     float* Ldet = nullptr;
     // per-level scratch (octave-0 sized, per image) unless keep_evolutions
     float* Lsmooth = nullptr;
+    float* Lsmooth2 = nullptr;  // second scratch (odd levels): detector(l) on its own stream may still read Lsmooth_l while
+                                // prep(l+1) writes Lsmooth_{l+1}
     float* Lflow = nullptr;
     float* Ltmp = nullptr;
     // keep_evolutions extras (plane layout)
@@ -179,6 +181,12 @@ size_t match_tc_db_image_bytes(uint64_t ndb);
 int match_tc_parts(uint64_t nq, uint64_t ndb);
 int launch_match_tc(cudaStream_t s, const uint8_t* d_q, uint64_t nq, const uint8_t* d_db, uint64_t ndb, uint32_t db_index_base,
                     uint8_t* q_img, uint8_t* db_img, akz_top2* d_out, int n_parts);
+
+// where level `level`'s Lsmooth lives: per-level slabs when evolutions are kept, else one of two scratch planes by parity
+static inline float* lsmooth_slab(const Plan& P, const Buffers& B, int batch, int level) {
+    if (B.keep) return B.Lsmooth + (size_t)P.dev.lv[level].off * (size_t)batch;
+    return (level & 1) ? B.Lsmooth2 : B.Lsmooth;
+}
 
 // helpers to address [level][image] slabs
 static inline size_t plane_off(const Plan& P, int batch, int level, int img) {

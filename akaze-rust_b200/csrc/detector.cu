@@ -1044,7 +1044,7 @@ int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level)
     p.fast = fast ? 1 : 0;
     const size_t off = (size_t)lv.off * L.batch;
     // level 0: Lsmooth is Lt (lib.rs:58)
-    const float* ls = (level == 0) ? B.Lt : (B.keep ? B.Lsmooth + off : B.Lsmooth);
+    const float* ls = (level == 0) ? B.Lt : lsmooth_slab(P, B, L.batch, level);
     unsigned int* mk = B.mask + lv.mask_off;
     // streaming kernel: additionally needs the candidate rows (and their two neighbours) to be rows the passes compute
     static const bool force_tile = getenv("AKZ_DETECTOR_TILE") != nullptr;  // A/B switch for profiling

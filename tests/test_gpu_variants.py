@@ -55,7 +55,8 @@ def test_kernel_variants_agree(akz):
     base = run_variant({})
     assert all(n > 100 for _h, n in base.values()), base
     for env in ({"AKZ_DET_SMEM": "1"}, {"AKZ_FED_OLD": "1"}, {"AKZ_NO_CONTRAST_FUSION": "1"}, {"AKZ_DETECTOR_TILE": "1"},
-                {"AKZ_FED_MAXT": "8"}, {"AKZ_SERIAL_LANES": "1"}, {"AKZ_DEDUP_SINGLE": "1"}, {"AKZ_NO_RAMP": "1"}):
+                {"AKZ_FED_MAXT": "8"}, {"AKZ_SERIAL_LANES": "1"}, {"AKZ_DEDUP_SINGLE": "1"}, {"AKZ_NO_RAMP": "1"}, {"AKZ_DET_INLINE": "1"}, {"AKZ_NO_G2_FUSION": "1"},
+                {"AKZ_DEDUP_GROUPS": "16"}):
         assert run_variant(env) == base, env
 
 
