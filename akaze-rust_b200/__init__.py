@@ -18,7 +18,10 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libakaze_b200.so")
+# AKZ_FAST_MATH=1 (read once, at import) selects the opt-in build whose stencil kernels use fused multiply-adds: faster,
+# no longer bit-identical to the reference (inside the north-star tolerances; tools/fast_math_report.py). Default: exact.
+FAST_MATH = os.environ.get("AKZ_FAST_MATH", "0") not in ("", "0")
+LIB_PATH = os.path.join(_HERE, "libakaze_b200_fast.so" if FAST_MATH else "libakaze_b200.so")
 
 DESCRIPTOR_STRIDE = 64
 AKZ_KEEP_EVOLUTIONS = 1

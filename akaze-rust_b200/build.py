@@ -15,6 +15,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libakaze_b200.so")
+LIB_FAST = os.path.join(HERE, "libakaze_b200_fast.so")  # opt-in AKZ_FAST_MATH build (fused multiply-adds in the stencils)
+FAST_SOURCES = ("scale_space.cu", "detector.cu")        # the only sources that see -DAKZ_FAST_MATH
 SOURCES = ["akaze_api.cu", "scale_space.cu", "detector.cu", "keypoints.cu", "matcher.cu", "matcher_tc.cu"]
 HEADERS = ["common.cuh", "tile_util.cuh", "nccl_dyn.h", os.path.join("..", "..", "include", "akaze_b200.h")]
 
@@ -36,8 +38,8 @@ def _deps(src):
     return [os.path.join(CSRC, src)] + [os.path.join(CSRC, h) for h in HEADERS] + [os.path.abspath(__file__)]
 
 
-def _obj(src):
-    return os.path.join(OBJ, src.replace(".cu", ".o"))
+def _obj(src, fast=False):
+    return os.path.join(OBJ, src.replace(".cu", "_fast.o" if fast and src in FAST_SOURCES else ".o"))
 
 
 def _stale(target, deps):
@@ -47,21 +49,24 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def is_stale():
-    return _stale(LIB, [d for s in SOURCES for d in _deps(s)])
+def is_stale(fast=False):
+    return _stale(LIB_FAST if fast else LIB, [d for s in SOURCES for d in _deps(s)])
 
 
-def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a into one shared library. Returns its path."""
-    if not force and not is_stale():
-        return LIB
+def build(force=False, verbose=False, fast=False):
+    """Compile every CUDA source for sm_100a into one shared library. Returns its path. fast=True builds the opt-in
+    fused-multiply-add variant of the stencil kernels (libakaze_b200_fast.so; never loaded unless AKZ_FAST_MATH=1)."""
+    lib = LIB_FAST if fast else LIB
+    if not force and not is_stale(fast):
+        return lib
     os.makedirs(OBJ, exist_ok=True)
     nvcc = nvcc_path()
 
     def compile_one(src):
-        if not force and not _stale(_obj(src), _deps(src)):
+        if not force and not _stale(_obj(src, fast), _deps(src)):
             return ""
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", _obj(src)]
+        extra = ["-DAKZ_FAST_MATH"] if fast and src in FAST_SOURCES else []
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", _obj(src, fast)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("nvcc failed on %s:\n%s%s" % (src, r.stdout, r.stderr))
@@ -71,12 +76,12 @@ def build(force=False, verbose=False):
         logs = list(ex.map(compile_one, SOURCES))
     if verbose:
         print("\n".join(logs))
-    r = subprocess.run([nvcc, "-shared", "-o", LIB] + [_obj(s) for s in SOURCES] + ["-ldl"], capture_output=True, text=True)
+    r = subprocess.run([nvcc, "-shared", "-o", lib] + [_obj(s, fast) for s in SOURCES] + ["-ldl"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
-    return LIB
+    return lib
 
 
 if __name__ == "__main__":
     import sys
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, fast="--fast" in sys.argv))

@@ -647,11 +647,18 @@ __device__ __forceinline__ void det_stream_step(const DetStreamCtx<S>& k, DetStr
         sub2(R.cc[2], R.cc[3], cm[2], cm[3], lxx4[2], lxx4[3]);
         mul2v(lxx4[0], lxx4[1], lyy4[0], lyy4[1], p1[0], p1[1]);
         mul2v(lxx4[2], lxx4[3], lyy4[2], lyy4[3], p1[2], p1[3]);
+#ifndef AKZ_FAST_MATH
         mul2v(lxy4[0], lxy4[1], lxy4[0], lxy4[1], p2[0], p2[1]);
         mul2v(lxy4[2], lxy4[3], lxy4[2], lxy4[3], p2[2], p2[3]);
+#endif
 #pragma unroll
         for (int j = 0; j < 4; j++) {
+#ifdef AKZ_FAST_MATH
+            df[j] = fmaf(-lxy4[j], lxy4[j], p1[j]);
+            (void)p2;
+#else
             df[j] = p1[j] - p2[j];
+#endif
             R.det_m[j] = R.det_0[j];
             R.det_0[j] = R.det_p[j];
         }

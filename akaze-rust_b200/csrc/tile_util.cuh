@@ -59,9 +59,32 @@ __device__ __forceinline__ void sub2(float a0, float a1, float b0, float b1, flo
         : "=f"(r0), "=f"(r1)
         : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
 }
+// AKZ_FAST_MATH (opt-in build, libakaze_b200_fast.so): the filters use packed fused multiply-adds -- one rounding per tap
+// instead of two, 3 instead of 7 instructions per pixel pair and 3-tap filter. Results then differ from the reference in
+// the last bits (tools/fast_math_report.py measures by how much); the default build never defines it.
+__device__ __forceinline__ void fma2(float a0, float a1, float k, float c0, float c1, float& r0, float& r1) {
+    asm("{.reg .b64 ra, rk, rc, rr;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rk, {%4, %4};\n\t"
+        "mov.b64 rc, {%5, %6};\n\t"
+        "fma.rn.f32x2 rr, ra, rk, rc;\n\t"
+        "mov.b64 {%0, %1}, rr;}"
+        : "=f"(r0), "=f"(r1)
+        : "f"(a0), "f"(a1), "f"(k), "f"(c0), "f"(c1));
+}
 // out[j] = (k0 * a[j] + k1 * b[j]) + k2 * c[j], j = 0..3, in tap order (products packed in pairs, sums scalar)
 __device__ __forceinline__ void tap3x4(float k0, float k1, float k2, const float (&a)[4], const float (&b)[4], const float (&c)[4],
                                        float (&out)[4]) {
+#ifdef AKZ_FAST_MATH
+#pragma unroll
+    for (int j = 0; j < 4; j += 2) {
+        float p0, p1;
+        mul2(a[j], a[j + 1], k0, p0, p1);
+        fma2(b[j], b[j + 1], k1, p0, p1, p0, p1);
+        fma2(c[j], c[j + 1], k2, p0, p1, out[j], out[j + 1]);
+    }
+    return;
+#endif
 #pragma unroll
     for (int j = 0; j < 4; j += 2) {
         float pa0, pa1, pb0, pb1, pc0, pc1;
@@ -76,6 +99,18 @@ __device__ __forceinline__ void tap3x4(float k0, float k1, float k2, const float
 // out[j] = (((k0 * a[j] + k1 * b[j]) + k2 * c[j]) + k3 * d[j]) + k4 * e[j], the 5-tap form of tap3x4
 __device__ __forceinline__ void tap5x4(float k0, float k1, float k2, float k3, float k4, const float (&a)[4], const float (&b)[4],
                                        const float (&c)[4], const float (&d)[4], const float (&e)[4], float (&out)[4]) {
+#ifdef AKZ_FAST_MATH
+#pragma unroll
+    for (int j = 0; j < 4; j += 2) {
+        float p0, p1;
+        mul2(a[j], a[j + 1], k0, p0, p1);
+        fma2(b[j], b[j + 1], k1, p0, p1, p0, p1);
+        fma2(c[j], c[j + 1], k2, p0, p1, p0, p1);
+        fma2(d[j], d[j + 1], k3, p0, p1, p0, p1);
+        fma2(e[j], e[j + 1], k4, p0, p1, out[j], out[j + 1]);
+    }
+    return;
+#endif
 #pragma unroll
     for (int j = 0; j < 4; j += 2) {
         float pa0, pa1, pb0, pb1, pc0, pc1, pd0, pd1, pe0, pe1;

@@ -421,11 +421,11 @@ def run_extract(args, images, h, w, n_img, full):
     tot_ms = sum(v[0] for v in st.values())
     sum_px = px * (1 + 0.25 + 0.0625 + 0.015625) * 4  # all 16 levels
     alg = {  # algorithmic HBM bytes per image of each stage as implemented
-        "fed": 12.0 * fed_chunks_px(px),
-        "detector": 16.0 * sum_px,
-        "prep": 12.0 * (sum_px - px),
+        "fed": 12.0 * fed_chunks_px(px) + 4.0 * px,  # level 1 reads the stored gradients (8 B/px) instead of Lflow (4)
+        "detector": 16.0 * sum_px,                   # read Lsmooth, write Lx, Ly, Ldet
+        "prep": 12.0 * (sum_px - 2 * px) + 12.0 * (px / 4 + px / 16 + px / 64),  # levels 2..15: read Lt (16 B/px when halving), write Lsmooth + Lflow
         "level0": 5.0 * px,
-        "contrast": 8.0 * px,
+        "contrast": 24.0 * px,                       # read Lt0, write Lsmooth1 + gx + gy, re-read gx + gy for the histogram
         # gathers of the keypoint stages (mostly L2 hits; the planes they sample were just written):
         "descriptor": kp_per_image * (1241 * 12.0 + 28 + 64),   # 1241 samples x (Lt, Lx, Ly) + keypoint in, descriptor out
         "finalize": kp_per_image * (109 * 8.0 + 5 * 4.0 + 28),  # 109 orientation samples x (Lx, Ly), 5 Ldet reads, keypoint out
