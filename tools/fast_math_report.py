@@ -40,8 +40,10 @@ def child(args):
         tot["oracle_kp"] += len(kr)
         tot["engine_kp"] += len(kg)
         if len(kg) and len(kr):
-            t = cKDTree(np.stack([kg["x"], kg["y"]], axis=1))
-            d, j = t.query(np.stack([kr["x"], kr["y"]], axis=1))
+            # nearest engine keypoint of the SAME class (several classes can hold a keypoint at one position): the class is
+            # folded into the tree as a third coordinate far larger than any image
+            t = cKDTree(np.stack([kg["x"], kg["y"], kg["class_id"] * 1.0e5], axis=1))
+            d, j = t.query(np.stack([kr["x"], kr["y"], kr["class_id"] * 1.0e5], axis=1))
             ok = (d <= 0.5) & (kg["octave"][j] == kr["octave"])
             tot["agree"] += int(ok.sum())
             same = ok & (kg["x"][j] == kr["x"]) & (kg["y"][j] == kr["y"]) & (kg["response"][j] == kr["response"])
