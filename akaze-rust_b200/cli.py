@@ -7,9 +7,9 @@
 File formats are akaze-util's (formats.py: ".json" -> serde_json layout, anything else -> bincode 1.1), the option file
 of `-o` is the serde_json form of `Config` and is WRITTEN with the defaults when it does not exist, like the reference
 (extract_features.rs:69-84). The matcher parameters are the reference's constants (0.86, 1000 RANSAC trials, 3.0 px);
-`-t` is parsed and logged but, as in the reference, not used (match_features.rs:57-78). The image outputs of `-d` and
-`-m` (scale-space PNG dump, keypoint / match overlays) are visualisation code outside the hot path:
-`-d` writes the evolution images as float32 .npy files instead, `-m` is accepted and reported as unsupported.
+`-t` is parsed and logged but, as in the reference, not used (match_features.rs:57-78). `-d` writes the scale space as
+normalised PNGs and the keypoint overlay, `-m` the match image (visualize.py mirrors the crate's drawing helpers; Lt and
+Ldet are also written as float32 .npy for numeric inspection).
 """
 import argparse
 import json
@@ -61,13 +61,22 @@ def cmd_extract_features(args, A=None):
     formats.serialize_features_to_file(keypoints, descriptors, args.OUTPUT)
     log.info("Done, extracted %d features.", len(keypoints))
     if args.debug_path:
+        # extract_features.rs:88-102: the scale space as normalised PNGs (write_evolutions) and the keypoint overlay
+        from akaze_rust_b200 import visualize
         os.makedirs(args.debug_path, exist_ok=True)
-        for i, e in enumerate(evolutions):
-            for name in ("Lt", "Lsmooth", "Lx", "Ly", "Lflow", "Ldet"):
-                img = getattr(e, name, None)  # level 0 has 0x0 Lflow, like the reference: nothing to write
+        written = visualize.write_evolutions(evolutions, args.debug_path)
+        for i, e in enumerate(evolutions):  # the float images themselves, for numeric inspection
+            for name in ("Lt", "Ldet"):
+                img = getattr(e, name, None)
                 if img is not None and np.size(img):
                     np.save(os.path.join(args.debug_path, "%s_%02d.npy" % (name, i)), np.asarray(img, np.float32))
-        log.info("Wrote the scale space as .npy files to %s (the PNG dumps of the reference are out of scope).", args.debug_path)
+        from akaze_rust_b200 import load_gray  # host code: decode + to_luma
+        from PIL import Image
+        try:
+            Image.fromarray(visualize.draw_keypoints(load_gray(args.INPUT), keypoints)).save(os.path.join(args.debug_path, "keypoints.png"))
+        except IndexError as e:  # a circle left the image: the reference panics here; the dump above is already written
+            log.warning("keypoint overlay not written: %s", e)
+        log.info("Wrote %d scale-space images to %s.", len(written), args.debug_path)
     return 0
 
 
@@ -105,8 +114,12 @@ def cmd_extract_and_match(args, A=None):
     m = A.match_features(feats[0][0], feats[0][1], feats[1][0], feats[1][1], 0.86, 1000, 3.0)
     log.info("Got %d matches.", len(m))
     formats.serialize_matches_to_file(m, paths[2])
-    if args.match_image:
-        log.warning("--match_image: drawing matches is visualisation code outside the hot path; not written.")
+    if args.match_image:  # extract_and_match.rs:110-121
+        from akaze_rust_b200 import load_gray, visualize
+        from PIL import Image
+        img = visualize.draw_matches(load_gray(args.INPUT_0), load_gray(args.INPUT_1), feats[0][0], feats[1][0], m)
+        Image.fromarray(img).save(args.match_image)
+        log.info("Wrote the match image to %s.", args.match_image)
     return 0
 
 

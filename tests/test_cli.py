@@ -75,7 +75,10 @@ def test_extract_and_match_and_match_features_tools(tmp_path, fake_api):
     assert cli.main(["extract_and_match", os.path.join(GOLD, "1.jpg"), os.path.join(GOLD, "2.jpg"), prefix, "-m", str(tmp_path / "m.png")],
                     fake_api) == 0
     names = sorted(os.listdir(tmp_path))
-    assert names == ["run-extractions_0.cbor", "run-extractions_1.cbor", "run-matches.cbor"]  # extract_and_match.rs:66-71
+    assert names == ["m.png", "run-extractions_0.cbor", "run-extractions_1.cbor", "run-matches.cbor"]  # extract_and_match.rs:66-71, -m
+    from PIL import Image
+    mi = Image.open(tmp_path / "m.png")
+    assert mi.size == (2 * 2016, 1512) and mi.mode == "RGB"  # draw_matches: both images side by side (feature_match.rs:44-47)
     m = formats.deserialize_matches_from_file(prefix + "-matches.cbor")
     put = fake_api.seen["putative"]
     assert 0 < len(m) <= len(put)

@@ -192,4 +192,9 @@ def test_cli_debug_dir_on_the_engine(akz, tmp_path):
     rc = cli.main(["extract_features", str(p), str(tmp_path / "out.bin"), "-d", str(tmp_path / "dbg")])
     assert rc == 0
     names = sorted(os.listdir(tmp_path / "dbg"))
-    assert "Lt_00.npy" in names and "Ldet_11.npy" in names and "Ldet_12.npy" not in names and "Lflow_01.npy" in names and "Lflow_00.npy" not in names
+    # write_evolutions' file names, reference quirk included (set_extension(".png") on "Lt_00000.png")
+    assert "Lt_00000..png" in names and "Ldet_00011..png" in names and "Ldet_00012..png" not in names
+    assert "Lflow_00001..png" in names and "Lflow_00000..png" not in names and "Lstep_00003..png" in names
+    assert "Lt_00.npy" in names and "keypoints.png" in names
+    png = np.asarray(Image.open(tmp_path / "dbg" / "Lt_00000..png"))
+    assert png.shape == img.shape and png.min() == 0 and png.max() == 255  # normalised to the full range

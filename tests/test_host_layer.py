@@ -2,6 +2,7 @@
 argument validation that must not reach the library, the C ABI's symbol list."""
 import os
 import re
+import types
 
 import numpy as np
 import pytest
@@ -109,3 +110,39 @@ def test_rust_overlay_lists_every_source_and_symbol(akz):
     for const in set(re.findall(r"ffi::(AKZ_\w+)", lib_rs)):
         assert re.search(r"pub const %s\b" % const, ffi), const
     assert not os.path.exists(os.path.join(rust, "src", "types")) and "download_all(f" in lib_rs and "unsafe fn download_all" in lib_rs
+
+
+def test_visualisation_helpers_follow_the_reference(akz, tmp_path):
+    """types/image.rs:148-210,385-480, evolution.rs:163-218, keypoint.rs:52-72, feature_match.rs:32-82."""
+    from akaze_rust_b200 import visualize as V
+    a = np.array([[0.25, 0.5], [0.75, 1.25]], np.float32)
+    n = V.normalize(a)
+    assert n.dtype == np.float32 and n.min() == 0.0 and n.max() == 1.0 and n[0, 1] == np.float32(0.25) / np.float32(1.0)
+    assert np.array_equal(V.create_dynamic_image(np.array([[0.0, 0.5, 0.999, 1.0]], np.float32)), [[0, 127, 254, 255]])  # truncating cast
+    assert V.build_path(tmp_path, "Lt_", 3).endswith("Lt_00003..png")  # the reference's set_extension(".png") quirk
+    assert V.save(np.zeros((0, 0), np.float32), str(tmp_path / "empty.png")) is False  # 0x0 images are skipped
+    assert V.save(a, str(tmp_path / "a.png")) and os.path.getsize(tmp_path / "a.png") > 0
+    assert V.random_color() == V.random_color()  # a fresh default source per call: one colour for everything
+    img = np.zeros((40, 60, 3), np.uint8)
+    V.draw_circle(img, (20.0, 20.0), (200, 100, 50), 5.0)
+    assert tuple(img[20, 20]) == (100, 50, 25)          # blend = truncated mean with the old pixel
+    assert tuple(img[20, 24]) == (100, 50, 25) and tuple(img[20, 25]) == (0, 0, 0)  # half-open pixel range: x in [15, 25)
+    assert tuple(img[15, 20]) == (100, 50, 25) and tuple(img[14, 20]) == (0, 0, 0)
+    with pytest.raises(IndexError):                      # the reference panics when a circle leaves the image
+        V.draw_circle(img, (58.0, 20.0), (1, 2, 3), 5.0)
+    img2 = np.zeros((40, 60, 3), np.uint8)
+    V.draw_line(img2, (10.0, 10.0), (40.0, 25.0), (255, 255, 255), 1.0)
+    assert img2[10, 10].any() and img2[17, 25].any() and not img2[30, 10].any()
+    k = np.zeros(2, akz.KEYPOINT_DTYPE)
+    k["x"], k["y"], k["size"] = (12.0, 30.0), (12.0, 20.0), (3.0, 4.0)
+    g0 = np.full((32, 48), 10, np.uint8)
+    over = V.draw_keypoints(g0, k)
+    assert over.shape == (32, 48, 3) and over[12, 12].tolist() != [10, 10, 10] and over[0, 0].tolist() == [10, 10, 10]
+    m = np.zeros(1, akz.MATCH_DTYPE)
+    m["index_0"], m["index_1"] = 0, 1
+    both = V.draw_matches(g0, np.full((40, 48), 20, np.uint8), k, k, m)
+    assert both.shape == (40, 96, 3) and both[0, 0, 0] == 10 and both[0, 48, 0] == 20 and both[35, 0, 0] == 0
+    ev = [types.SimpleNamespace(Lt=a, Lsmooth=a, Lx=a, Ly=a, Lxx=a, Lyy=a, Lxy=a, Lflow=np.zeros((0, 0), np.float32),
+                                Lstep=np.zeros((0, 0), np.float32), Ldet=a)]
+    written = V.write_evolutions(ev, tmp_path / "evo")
+    assert len(written) == 8 and os.path.exists(tmp_path / "evo" / "Ldet_00000..png")
