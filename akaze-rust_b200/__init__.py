@@ -88,7 +88,7 @@ EXPORTS = [
     "akz_features_evolution_download", "akz_features_free", "akz_match_top2", "akz_match_top2_device",
     "akz_merge_top2_device", "akz_descriptor_match",
     "akz_comm_unique_id", "akz_context_comm_init", "akz_context_comm_init_all", "akz_context_comm_destroy",
-    "akz_match_top2_sharded_device", "akz_match_top2_sharded",
+    "akz_match_top2_sharded_device", "akz_match_top2_sharded", "akz_remove_outliers",
 ]
 
 
@@ -168,6 +168,8 @@ def lib():
     L.akz_merge_top2_device.argtypes = [vp, vp, C.c_uint32, C.c_uint64, vp]
     L.akz_descriptor_match.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, C.c_uint32, C.c_size_t, C.c_uint64,
                                        C.c_double, vp, C.POINTER(C.c_uint64)]
+    L.akz_remove_outliers.argtypes = [vp, vp, C.c_uint64, vp, C.c_uint64, vp, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_int, vp,
+                                      C.POINTER(C.c_uint64), vp]
     L.akz_comm_unique_id.argtypes = [vp]
     L.akz_context_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
     L.akz_context_comm_init_all.argtypes = [C.POINTER(vp), C.c_int]
@@ -475,6 +477,25 @@ class Engine:
                                           stride, distance_threshold, lowes_ratio, out.ctypes.data, C.byref(n)))
         return out[:n.value].copy()
 
+    def remove_outliers(self, keypoints_0, keypoints_1, matches, num_trials, epsilon_model, epsilon_inlier, sampling="reference",
+                        return_model=False):
+        """ops::estimate_fundamental_matrix::remove_outliers (estimate_fundamental_matrix.rs:99-165) on the GPU, all trials in
+        parallel (akz_remove_outliers). sampling: "reference" = a fresh default random source per trial as the crate does (every
+        trial draws the same eight matches), "advancing" = one source across the trials."""
+        k0 = np.ascontiguousarray(keypoints_0, KEYPOINT_DTYPE)
+        k1 = np.ascontiguousarray(keypoints_1, KEYPOINT_DTYPE)
+        m = np.zeros(len(matches), MATCH_DTYPE)
+        for f in MATCH_DTYPE.names:
+            m[f] = matches[f]
+        out = np.zeros(max(len(m), 1), MATCH_DTYPE)
+        n = C.c_uint64()
+        model = np.zeros(9, np.float32)
+        _check(lib().akz_remove_outliers(self._h, k0.ctypes.data, len(k0), k1.ctypes.data, len(k1), m.ctypes.data, len(m), int(num_trials),
+                                         float(epsilon_model), float(epsilon_inlier), {"reference": 0, "advancing": 1}[sampling],
+                                         out.ctypes.data, C.byref(n), model.ctypes.data))
+        res = out[:n.value].copy()
+        return (res, model.reshape(3, 3)) if return_model else res
+
     # -- multi-GPU matching: database sharded by index over the ranks, NCCL all-gather + merge inside the library
     def comm_init(self, unique_id, rank, n_ranks):
         """Joins a communicator of n_ranks engines (one process per GPU); unique_id from comm_unique_id() of rank 0."""
@@ -573,10 +594,14 @@ def descriptor_match(descriptors_0, descriptors_1, distance_threshold=10000, low
 
 
 def match_features(keypoints_0, descriptors_0, keypoints_1, descriptors_1, lowes_ratio, ransac_trials,
-                   ransac_epsilon_inliers, engine=None, seed=None):
-    """akaze::match_features (lib.rs:252-275): brute-force matching on the GPU, then the reference's
-    RANSAC outlier removal on the host (remove_outliers stays host code)."""
-    from . import ransac
+                   ransac_epsilon_inliers, engine=None, seed=None, ransac="host"):
+    """akaze::match_features (lib.rs:252-275): brute-force matching on the GPU, then the reference's RANSAC outlier removal:
+    ransac="host" runs the numpy restatement (ransac.py), "gpu" / "gpu-advancing" run akz_remove_outliers (all trials in parallel,
+    with the crate's sampling or with one random source advanced across the trials)."""
     output = descriptor_match(descriptors_0, descriptors_1, 10000, lowes_ratio, engine=engine)
-    return ransac.remove_outliers(keypoints_0, keypoints_1, output, ransac_trials, 0.05, ransac_epsilon_inliers,
-                                  seed=seed)
+    if ransac in ("gpu", "gpu-advancing"):
+        eng = engine or default_engine()
+        return eng.remove_outliers(keypoints_0, keypoints_1, output, ransac_trials, 0.05, ransac_epsilon_inliers,
+                                   sampling="advancing" if ransac == "gpu-advancing" else "reference")
+    from . import ransac as ransac_host
+    return ransac_host.remove_outliers(keypoints_0, keypoints_1, output, ransac_trials, 0.05, ransac_epsilon_inliers, seed=seed)

@@ -17,7 +17,7 @@ OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libakaze_b200.so")
 LIB_FAST = os.path.join(HERE, "libakaze_b200_fast.so")  # opt-in AKZ_FAST_MATH build (fused multiply-adds in the stencils)
 FAST_SOURCES = ("scale_space.cu", "detector.cu")        # the only sources that see -DAKZ_FAST_MATH
-SOURCES = ["akaze_api.cu", "scale_space.cu", "detector.cu", "keypoints.cu", "matcher.cu", "matcher_tc.cu"]
+SOURCES = ["akaze_api.cu", "scale_space.cu", "detector.cu", "keypoints.cu", "matcher.cu", "matcher_tc.cu", "ransac.cu"]
 HEADERS = ["common.cuh", "tile_util.cuh", "nccl_dyn.h", os.path.join("..", "..", "include", "akaze_b200.h")]
 
 NVCC_FLAGS = [

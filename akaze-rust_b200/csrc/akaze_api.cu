@@ -1378,6 +1378,110 @@ int akz_descriptor_match(akz_context* c, const uint8_t* d0, uint64_t n0, const u
     return AKZ_OK;
 }
 
+// ---- RANSAC -----------------------------------------------------------------------------
+namespace {
+struct Xorshift128Plus {  // the `random` crate's default source (xorshift128+ seeded [42, 69]); ^0.12 is not under /root/reference
+    uint64_t s0 = 42, s1 = 69;
+    uint64_t read_u64() {
+        uint64_t x = s0;
+        const uint64_t y = s1;
+        s0 = y;
+        x ^= x << 23;
+        x ^= x >> 17;
+        x ^= y ^ (y >> 26);
+        s1 = x;
+        return x + y;
+    }
+};
+}  // namespace
+
+int akz_remove_outliers(akz_context* c, const akz_keypoint* kp0, uint64_t n0, const akz_keypoint* kp1, uint64_t n1, const akz_match* matches,
+                        uint64_t n_matches, uint64_t num_trials, float epsilon_model, float epsilon_inlier, int sampling, akz_match* out,
+                        uint64_t* n_out, float* model) {
+    if (!c || !n_out || (n_matches && (!matches || !out || !kp0 || !kp1))) return fail(AKZ_ERR_INVALID, "null argument");
+    if (sampling != AKZ_RANSAC_REFERENCE && sampling != AKZ_RANSAC_ADVANCING) return fail(AKZ_ERR_INVALID, "bad sampling policy");
+    *n_out = 0;
+    if (model) memset(model, 0, 9 * sizeof(float));
+    if (n_matches < 8) {  // estimate_fundamental_matrix.rs:107-110: not enough points, the matches come back untouched
+        for (uint64_t i = 0; i < n_matches; i++) out[i] = matches[i];
+        *n_out = n_matches;
+        return AKZ_OK;
+    }
+    if (n_matches > 0xffffffffull || num_trials > (1ull << 24)) return fail(AKZ_ERR_CAPACITY, "too many matches or trials");
+    std::vector<float2> pl(n_matches), pr(n_matches);
+    for (uint64_t i = 0; i < n_matches; i++) {
+        if (matches[i].index_0 >= n0 || matches[i].index_1 >= n1) return fail(AKZ_ERR_INVALID, "match index outside the keypoint arrays");
+        pl[i] = make_float2(kp0[matches[i].index_0].x, kp0[matches[i].index_0].y);
+        pr[i] = make_float2(kp1[matches[i].index_1].x, kp1[matches[i].index_1].y);
+    }
+    // which eight matches every trial draws (:116-125), ascending inside a trial
+    const uint32_t nt = (uint32_t)num_trials;
+    std::vector<unsigned int> samples((size_t)nt * 8);
+    Xorshift128Plus running;
+    for (uint32_t t = 0; t < nt; t++) {
+        Xorshift128Plus fresh;
+        Xorshift128Plus& src = sampling == AKZ_RANSAC_REFERENCE ? fresh : running;
+        unsigned int chosen[8];
+        int k = 0;
+        while (k < 8) {
+            const unsigned int v = (unsigned int)(src.read_u64() % n_matches);
+            bool dup = false;
+            for (int j = 0; j < k; j++) dup = dup || chosen[j] == v;
+            if (!dup) chosen[k++] = v;
+        }
+        std::sort(chosen, chosen + 8);
+        memcpy(&samples[(size_t)t * 8], chosen, sizeof(chosen));
+    }
+    LOCK(c);
+    CK(cudaSetDevice(c->device));
+    const size_t b_pts = n_matches * sizeof(float2), b_smp = samples.size() * sizeof(unsigned int);
+    const size_t b_models = (size_t)(nt + 1) * 9 * sizeof(float), b_u32 = (size_t)nt * sizeof(unsigned int);
+    const size_t need = 2 * b_pts + b_smp + b_models + 2 * b_u32 + n_matches + 256;
+    int rc = grow(&c->m_parts, &c->m_parts_cap, need);  // the matcher's scratch: no match job is in flight on a locked context
+    if (rc != AKZ_OK) return rc;
+    char* base = (char*)c->m_parts;
+    float2* d_pl = (float2*)base;
+    float2* d_pr = (float2*)(base + b_pts);
+    float* d_models = (float*)(base + 2 * b_pts);                      // [nt] + the final model behind them
+    unsigned int* d_samples = (unsigned int*)(base + 2 * b_pts + b_models);
+    unsigned int* d_ok = (unsigned int*)((char*)d_samples + b_smp);
+    unsigned int* d_counts = d_ok + nt;
+    unsigned char* d_mask = (unsigned char*)(d_counts + nt);
+    CK(cudaMemcpyAsync(d_pl, pl.data(), b_pts, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_pr, pr.data(), b_pts, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(d_samples, samples.data(), b_smp, cudaMemcpyHostToDevice, c->stream));
+    c->launches += launch_ransac_models(c->stream, d_pl, d_pr, d_samples, nt, epsilon_model, d_models, d_ok);
+    c->launches += launch_ransac_count(c->stream, d_pl, d_pr, (unsigned int)n_matches, d_models, d_ok, nt, epsilon_inlier, d_counts);
+    std::vector<unsigned int> counts(nt), ok(nt);
+    CK(cudaMemcpyAsync(counts.data(), d_counts, b_u32, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(ok.data(), d_ok, b_u32, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    // :150-153: the first trial with a strictly larger inlier count wins; without any model final_model stays all zeros
+    unsigned int best = 0;
+    int best_t = -1;
+    for (uint32_t t = 0; t < nt; t++)
+        if (ok[t] && counts[t] > best) {
+            best = counts[t];
+            best_t = (int)t;
+        }
+    float* d_final = d_models + (size_t)nt * 9;
+    float final_model[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (best_t >= 0) CK(cudaMemcpyAsync(final_model, d_models + (size_t)best_t * 9, sizeof(final_model), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpyAsync(d_final, final_model, sizeof(final_model), cudaMemcpyHostToDevice, c->stream));
+    c->launches += launch_ransac_mask(c->stream, d_pl, d_pr, (unsigned int)n_matches, d_final, epsilon_inlier, d_mask);
+    std::vector<unsigned char> mask(n_matches);
+    CK(cudaMemcpyAsync(mask.data(), d_mask, n_matches, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaGetLastError());
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < n_matches; i++)
+        if (mask[i]) out[k++] = matches[i];
+    *n_out = k;
+    if (model) memcpy(model, final_model, sizeof(final_model));
+    return AKZ_OK;
+}
+
 // ---- multi-GPU matching -------------------------------------------------------
 // The database is partitioned contiguously by index over the ranks (one context per GPU), the queries are replicated.
 // Every rank computes its shard's top-2 records, the 8-byte records are all-gathered with NCCL over NVLink (8 MB per

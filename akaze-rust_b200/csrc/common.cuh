@@ -188,6 +188,14 @@ static inline float* lsmooth_slab(const Plan& P, const Buffers& B, int batch, in
     return (level & 1) ? B.Lsmooth2 : B.Lsmooth;
 }
 
+// ransac.cu
+int launch_ransac_models(cudaStream_t s, const float2* pl, const float2* pr, const unsigned int* samples, unsigned int n_trials,
+                         float epsilon, float* models, unsigned int* ok);
+int launch_ransac_count(cudaStream_t s, const float2* pl, const float2* pr, unsigned int n_matches, const float* models,
+                        const unsigned int* ok, unsigned int n_trials, float epsilon_inlier, unsigned int* counts);
+int launch_ransac_mask(cudaStream_t s, const float2* pl, const float2* pr, unsigned int n_matches, const float* model, float epsilon_inlier,
+                       unsigned char* mask);
+
 // helpers to address [level][image] slabs
 static inline size_t plane_off(const Plan& P, int batch, int level, int img) {
     return (size_t)P.dev.lv[level].off * (size_t)batch + (size_t)img * (size_t)P.dev.lv[level].w * P.dev.lv[level].h;

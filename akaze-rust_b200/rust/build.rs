@@ -9,7 +9,7 @@ fn main() {
     let csrc = env::var("AKAZE_B200_CSRC").map(PathBuf::from).unwrap_or_else(|_| PathBuf::from(env::var("CARGO_MANIFEST_DIR").unwrap()).join("../csrc"));
     let lib = out.join("libakaze_b200.so");
     // every source of akaze-rust_b200/build.py (tests/test_host_layer.py keeps the two lists equal)
-    let sources = ["akaze_api.cu", "scale_space.cu", "detector.cu", "keypoints.cu", "matcher.cu", "matcher_tc.cu"];
+    let sources = ["akaze_api.cu", "scale_space.cu", "detector.cu", "keypoints.cu", "matcher.cu", "matcher_tc.cu", "ransac.cu"];
     let mut cmd = Command::new(env::var("NVCC").unwrap_or_else(|_| "nvcc".into()));
     cmd.args(&["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "--fmad=false",
                "-std=c++17", "-Xcompiler", "-fPIC", "-shared", "-ldl", "-o"]).arg(&lib);

@@ -204,6 +204,22 @@ int akz_descriptor_match(akz_context *ctx, const uint8_t *d0, uint64_t n0, const
                          uint32_t desc_len, size_t stride, uint64_t distance_threshold, double lowes_ratio,
                          akz_match *out, uint64_t *n_out);
 
+/* ---- RANSAC: replaces ops::estimate_fundamental_matrix::remove_outliers
+ *      (akaze/src/ops/estimate_fundamental_matrix.rs:99-165; with estimate_fundamental_matrix :17-69 and
+ *      evaluate_model :79-83), the second half of akaze::match_features (lib.rs:267-274). All trials run
+ *      in parallel: one thread per hypothesis (8 x 9 system, SVD, rank test), one block per hypothesis for
+ *      the inlier count. Fewer than 8 matches are returned untouched (:107-110).
+ *      The reference builds a FRESH default random source on every trial (:118), so all its trials draw the
+ *      same eight matches: AKZ_RANSAC_REFERENCE reproduces that, AKZ_RANSAC_ADVANCING runs one source on
+ *      across the trials (num_trials distinct hypotheses). The source is the `random` crate's default,
+ *      xorshift128+ seeded [42, 69] (third party, unpinned); the eight matches are used in ascending index
+ *      order (the reference's HashSet order is process-random). kp0 / kp1: the keypoint arrays the matches
+ *      index; out must hold n_matches entries; model (may be NULL) receives the winning 3x3 matrix row by row. */
+enum akz_ransac_sampling { AKZ_RANSAC_REFERENCE = 0, AKZ_RANSAC_ADVANCING = 1 };
+int akz_remove_outliers(akz_context *ctx, const akz_keypoint *kp0, uint64_t n0, const akz_keypoint *kp1, uint64_t n1,
+                        const akz_match *matches, uint64_t n_matches, uint64_t num_trials, float epsilon_model,
+                        float epsilon_inlier, int sampling, akz_match *out, uint64_t *n_out, float *model);
+
 /* ---- multi-GPU matching: the database is partitioned contiguously by index over the
  *      GPUs, queries are replicated, every GPU runs the top-2 scan on its shard, the 8-byte records are
  *      all-gathered with NCCL over NVLink and merged with the sequential scan's tie rule (lowest index),

@@ -349,13 +349,40 @@ inline std::vector<Match> remove_outliers(const std::vector<Keypoint>& k0, const
     return inliers;
 }
 
+// remove_outliers on the GPU (akz_remove_outliers): every trial's hypothesis and inlier count in parallel. With
+// AKZ_RANSAC_REFERENCE it returns exactly what remove_outliers above returns (same samples, same Jacobi SVD, same operation
+// order); AKZ_RANSAC_ADVANCING lets the random source run on across the trials, i.e. num_trials distinct hypotheses.
+inline std::vector<Match> remove_outliers_b200(const std::vector<Keypoint>& k0, const std::vector<Keypoint>& k1, const std::vector<Match>& matches,
+                                               size_t num_trials, float epsilon_model, float epsilon_inlier, int sampling = AKZ_RANSAC_REFERENCE,
+                                               Engine& engine = default_engine(), Matrix3* model = nullptr) {
+    auto pack = [](const std::vector<Keypoint>& k) {
+        std::vector<akz_keypoint> r(k.size());
+        for (size_t i = 0; i < k.size(); i++)
+            r[i] = akz_keypoint{k[i].point.first, k[i].point.second, k[i].response, k[i].size, (uint32_t)k[i].octave, (uint32_t)k[i].class_id, k[i].angle};
+        return r;
+    };
+    const std::vector<akz_keypoint> a = pack(k0), b = pack(k1);
+    std::vector<akz_match> in(matches.size()), out(std::max<size_t>(matches.size(), 1));
+    for (size_t i = 0; i < matches.size(); i++) in[i] = akz_match{(uint64_t)matches[i].index_0, (uint64_t)matches[i].index_1, matches[i].distance};
+    uint64_t n = 0;
+    float f[9];
+    if (akz_remove_outliers(engine.get(), a.data(), a.size(), b.data(), b.size(), in.data(), in.size(), num_trials, epsilon_model, epsilon_inlier,
+                            sampling, out.data(), &n, f) != AKZ_OK)
+        fail("remove_outliers");
+    if (model)
+        for (int i = 0; i < 9; i++) model->m[i / 3][i % 3] = f[i];
+    std::vector<Match> r(n);
+    for (uint64_t i = 0; i < n; i++) r[i] = Match{(size_t)out[i].index_0, (size_t)out[i].index_1, out[i].distance};
+    return r;
+}
+
 // akaze::match_features (lib.rs:252-275): descriptor_match with the hard-wired distance threshold 10000, then RANSAC
-// with epsilon_model = 1e-7 (lib.rs:264-273)
+// with epsilon_model = 0.05 (lib.rs:267-274)
 inline std::vector<Match> match_features(const std::vector<Keypoint>& keypoints_0, const std::vector<Descriptor>& descriptors_0,
                                          const std::vector<Keypoint>& keypoints_1, const std::vector<Descriptor>& descriptors_1,
                                          double lowes_ratio, size_t ransac_trials, float ransac_epsilon_inliers, Engine& engine = default_engine()) {
     const std::vector<Match> m = descriptor_match(descriptors_0, descriptors_1, 10000, lowes_ratio, engine);
-    return remove_outliers(keypoints_0, keypoints_1, m, ransac_trials, 1e-7f, ransac_epsilon_inliers);
+    return remove_outliers(keypoints_0, keypoints_1, m, ransac_trials, 0.05f, ransac_epsilon_inliers);
 }
 
 }  // namespace akaze

@@ -72,6 +72,19 @@ int main(int argc, char** argv) {
             akaze_util::serialize_matches_to_file(mf, out + "/matches.bin");
             std::printf("levels %zu %zu keypoints %zu %zu descriptor_matches %zu matches %zu tau0 %zu\n", e0.size(), e1.size(), kp0.size(), kp1.size(),
                         dm.size(), mf.size(), e0.size() > 1 ? e0[1].fed_tau_steps.size() : 0);
+            // RANSAC on the GPU: with the reference's sampling it must return exactly the host mirror's inliers; with an advancing
+            // source it tries 1000 distinct hypotheses, the first of which is the reference's, so it keeps at least as many
+            const std::vector<akaze::Match> host = akaze::remove_outliers(kp0, kp1, dm, 1000, 0.05f, 3.0f);
+            akaze::Matrix3 f_ref, f_adv;
+            const std::vector<akaze::Match> gpu = akaze::remove_outliers_b200(kp0, kp1, dm, 1000, 0.05f, 3.0f, AKZ_RANSAC_REFERENCE, eng, &f_ref);
+            const std::vector<akaze::Match> adv = akaze::remove_outliers_b200(kp0, kp1, dm, 1000, 0.05f, 3.0f, AKZ_RANSAC_ADVANCING, eng, &f_adv);
+            bool same = host.size() == gpu.size() && host.size() == mf.size();
+            for (size_t i = 0; same && i < host.size(); i++) same = host[i].index_0 == gpu[i].index_0 && host[i].index_1 == gpu[i].index_1;
+            // every match the advancing run kept is an inlier of the model it returned (evaluate_model on the host, same arithmetic)
+            size_t consistent = 0;
+            for (const akaze::Match& m : adv) consistent += akaze::evaluate_model(f_adv, kp0[m.index_0], kp1[m.index_1]) < 3.0f ? 1 : 0;
+            akaze_util::serialize_matches_to_file(adv, out + "/matches_ransac_advancing.bin");
+            std::printf("ransac host %zu gpu %zu same %d advancing %zu consistent %zu\n", host.size(), gpu.size(), same ? 1 : 0, adv.size(), consistent);
             return 0;
         }
     } catch (const std::exception& e) {

@@ -97,4 +97,19 @@ def test_cpp_mirror_matches_python_mirror(checker, akz, tmp_path):
     mf = F.deserialize_matches_from_file(tmp_path / "matches.bin")
     assert 0 < len(mf) <= len(dm)
     assert set(zip(mf["index_0"], mf["index_1"])).issubset(set(zip(dm["index_0"], dm["index_1"])))
+    # GPU RANSAC (akz_remove_outliers): identical to the host mirror under the reference's sampling, at least as
+    # many inliers with 1000 distinct hypotheses, and every kept match is an inlier of the returned model
+    line = [l for l in r.stdout.splitlines() if l.startswith("ransac host")][0].split()
+    host_n, gpu_n, same, adv_n, consistent = int(line[2]), int(line[4]), int(line[6]), int(line[8]), int(line[10])
+    assert same == 1 and host_n == gpu_n == len(mf)
+    assert adv_n >= gpu_n and consistent == adv_n
+    adv = F.deserialize_matches_from_file(tmp_path / "matches_ransac_advancing.bin")
+    assert set(zip(adv["index_0"], adv["index_1"])).issubset(set(zip(dm["index_0"], dm["index_1"])))
+    # the same through the Python layer
+    g = eng.remove_outliers(f0.keypoints, f1.keypoints, ref, 1000, 0.05, 3.0, sampling="reference")
+    assert np.array_equal(g["index_0"], mf["index_0"]) and np.array_equal(g["index_1"], mf["index_1"])
+    g2, model = eng.remove_outliers(f0.keypoints, f1.keypoints, ref, 1000, 0.05, 3.0, sampling="advancing", return_model=True)
+    assert np.array_equal(g2["index_0"], adv["index_0"]) and model.shape == (3, 3) and np.isfinite(model).all()
+    few = eng.remove_outliers(f0.keypoints, f1.keypoints, ref[:5], 1000, 0.05, 3.0)
+    assert np.array_equal(few, ref[:5])  # fewer than 8 matches come back untouched (estimate_fundamental_matrix.rs:107-110)
     eng.close()
