@@ -92,6 +92,22 @@ def test_raw_4k_frame_fits_default_capacities(akz, oracle):
     eng.close()
 
 
+def test_thirty_two_levels(akz, oracle):
+    """The most levels the engine admits (8 sublevels x 4 octaves = 32): the level-pipelined cache pass then runs one warp per
+    level in a 1024-thread block, in default mode and with every evolution kept."""
+    img = R.synthetic_image(480, 640, seed=23)
+    cg, co = akz.Config.default(), oracle.default_config()
+    cg.num_sublevels = co.num_sublevels = 8
+    ref = oracle.extract(oracle.unit_float_from_u8(img), co, threads=8)
+    assert ref.status == 0 and ref.num_levels == 32 and len(ref.keypoints) > 200
+    for keep in (False, True):
+        eng = akz.Engine(0, 640, 480, 1, keep_evolutions=keep)
+        f = eng.extract_u8(img, cg)
+        assert len(f.evolutions) == 32
+        _check_features(f, ref)
+        eng.close()
+
+
 def _literal_descriptor_match(d0, d1, T, lowes):
     """feature_matching.rs:23-94 with full distances (the bail-out never changes the outcome, see
     test_oracle_vs_numpy_keypoints.py)."""

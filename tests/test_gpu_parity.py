@@ -107,7 +107,8 @@ def test_non_default_configs(engine, oracle, akz):
     img = R.synthetic_image(200, 300, 41)
     for kw in ({"descriptor_channels": 1}, {"descriptor_channels": 2}, {"num_sublevels": 3, "max_octave_evolution": 2},
                {"detector_threshold": 0.0005, "contrast_percentile": 0.5, "contrast_factor_num_bins": 128},
-               {"base_scale_offset": 2.0, "derivative_factor": 1.2}):
+               {"base_scale_offset": 2.0, "derivative_factor": 1.2},
+               {"num_sublevels": 8, "max_octave_evolution": 4}):
         cg, co = akz.Config.default(), oracle.default_config()
         for k, v in kw.items():
             setattr(cg, k, v)
