@@ -469,6 +469,9 @@ static int ensure_lane(akz_context* c, Lane& ln, int batch) {
     CK(dalloc(A, &B.hmax_bits, nb));
     CK(dalloc(A, &B.hist, nb * kMaxBins));
     CK(dalloc(A, &B.contrast_thr, nb * (kMaxBins + 1)));
+    CK(dalloc(A, &B.fine_hist, nb * contrast_fine_bins()));
+    CK(dalloc(A, &B.contrast_resolved, nb));
+    CK(dalloc(A, &B.contrast_npoints, nb));
     CK(dalloc(A, &B.mask, (size_t)P.dev.mask_words * nb));
     CK(dalloc(A, &B.cand, (size_t)c->cand_cap * nb));
     size_t total_rows = 0;

@@ -108,6 +108,9 @@ struct Buffers {
     double* contrast_thr = nullptr;           // [B][kMaxBins + 1] smallest squared gradient magnitude that falls into bin b
     unsigned int* hist = nullptr;             // [B][n_bins]
     double* kcontrast = nullptr;              // [B][kMaxLevels] contrast factor per level
+    unsigned int* fine_hist = nullptr;        // [B][contrast_fine_bins()] hmax-independent fine histogram of g2 (scale_space.cu)
+    int* contrast_resolved = nullptr;         // [B] bins walked, decided from the fine histogram, or -1
+    unsigned long long* contrast_npoints = nullptr;  // [B]
     // candidates
     unsigned int* mask = nullptr;       // [B][mask_words]
     unsigned int* cand = nullptr;       // [B][cand_cap] packed flat index, level-major raster order
@@ -154,6 +157,7 @@ struct Launch {
 // scale_space.cu
 int launch_level0(const Launch& L, const Plan& P, const Buffers& B, const void* d_in, bool is_u8, size_t in_stride);
 int launch_contrast(const Launch& L, const Plan& P, const Buffers& B);
+size_t contrast_fine_bins();
 int launch_prep(const Launch& L, const Plan& P, const Buffers& B, int level);
 int launch_fed(const Launch& L, const Plan& P, const Buffers& B, int level);
 // detector.cu
