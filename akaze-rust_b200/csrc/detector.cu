@@ -496,36 +496,37 @@ struct RingSmem {
     __device__ __forceinline__ void fence5(float4&, float4&, float4&, float4&, float4&) const {}
 };
 
-template <int S>
+// NSM = how many of the five rings (in the order A, Bo, C, E, D) live in shared memory instead; the others take
+// (5 - NSM) * 2S * 4 tensor-memory columns of the warp's 32 lanes.
+template <int S, int NSM>
 struct RingTmem {
     static constexpr int D = StreamGeo<S>::D;
-    static constexpr bool A_IN_SMEM = (S == 4);
-    static constexpr int COLS = 128;  // allocation (power of two >= 32): 5 * 2S * 4 = 80 / 120 columns, or 4 * 8 * 4 = 128 for S = 4
-    unsigned int base;                // TMEM address: this warp's first lane, first column of the CTA's allocation
-    float4 (*ring_a)[32];             // S = 4 only: ring A of this warp in shared memory
+    static constexpr int COLS = (5 - NSM) * D * 4;  // tensor-memory columns one warp needs
+    unsigned int base;                // TMEM address: this warp's first lane, first of its columns
+    float4 (*ring_sm)[D][32];         // [NSM] rings of this warp in shared memory
     int lane;
-    // a ring row is named by a handle = the TMEM address of its four columns in array 0; the other arrays sit at
-    // compile-time column offsets that go into the instruction's immediate field (tmem[UR + imm]), so a steady row moves
-    // two handles to uniform registers instead of one address per access
+    // a ring row is named by a handle = the TMEM address of its four columns in the first tensor-memory array; the other
+    // arrays sit at compile-time column offsets that go into the instruction's immediate field (tmem[UR + imm]), so a steady
+    // row moves two handles to uniform registers instead of one address per access
     __device__ __forceinline__ int handle(int slot) const { return (int)(base + 4u * (unsigned int)slot); }
     __device__ __forceinline__ int next(int h) const { return (h + 4 == (int)(base + 4u * D)) ? (int)base : h + 4; }
     template <int A>
     __device__ __forceinline__ float4 load(int h) const {
-        if (A_IN_SMEM && A == 0) return ring_a[(h - (int)base) >> 2][lane];
+        if (A < NSM) return ring_sm[A < NSM ? A : 0][(h - (int)base) >> 2][lane];
         unsigned int r0, r1, r2, r3;
         asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4 + %5];"
                      : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
-                     : "r"(h), "n"((A_IN_SMEM ? A - 1 : A) * D * 4)
+                     : "r"(h), "n"((A < NSM ? 0 : A - NSM) * D * 4)
                      : "memory");
         return make_float4(__uint_as_float(r0), __uint_as_float(r1), __uint_as_float(r2), __uint_as_float(r3));
     }
     template <int A>
     __device__ __forceinline__ void store(int h, const float4& v) const {
-        if (A_IN_SMEM && A == 0) {
-            ring_a[(h - (int)base) >> 2][lane] = v;
+        if (A < NSM) {
+            ring_sm[A < NSM ? A : 0][(h - (int)base) >> 2][lane] = v;
             return;
         }
-        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0 + %1], {%2, %3, %4, %5};" ::"r"(h), "n"((A_IN_SMEM ? A - 1 : A) * D * 4),
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0 + %1], {%2, %3, %4, %5};" ::"r"(h), "n"((A < NSM ? 0 : A - NSM) * D * 4),
                      "r"(__float_as_uint(v.x)), "r"(__float_as_uint(v.y)), "r"(__float_as_uint(v.z)), "r"(__float_as_uint(v.w))
                      : "memory");
     }
@@ -845,32 +846,50 @@ k_detector_stream(const float* __restrict__ lsmooth, size_t img_px, float* __res
         det_stream_run<S, false>(k, rg, lq, c_begin, c_end);
 }
 
-// The same stream with the rings in tensor memory (RingTmem): four warps = four strips per CTA, 128 TMEM columns per CTA.
-constexpr int DT_WARPS = 4;
-template <int S>
-__global__ void __launch_bounds__(DT_WARPS * 32, 4)
+// The same stream with the rings in tensor memory (RingTmem). A warp reaches only the 32 tensor-memory lanes of its quarter
+// (warp id mod 4), so a CTA of WPC warps stacks WPC / 4 warps per quarter side by side in the columns.
+//   WPC = 4:  four warps, 128 columns per CTA, four CTAs per SM = 16 warps (ring A of S = 4 in shared memory)
+//   WPC = 20: one CTA per SM with all 512 columns, 20 warps at 96 registers (the kernel needs no more: 0 spill bytes); the
+//             rings that do not fit 512 / 5 = 102 columns per warp go to shared memory (none for S = 2, A for S = 3, A and Bo
+//             for S = 4)
+template <int S, int WPC>
+struct DetTmemCfg {
+    static constexpr int GROUPS = WPC / 4;  // warps per lane quarter
+    static constexpr int NSM = (WPC == 4) ? (S == 4 ? 1 : 0) : (S <= 2 ? 0 : (S == 3 ? 1 : 2));
+    using RT = RingTmem<S, NSM>;
+    static constexpr int NEED = GROUPS * RT::COLS;
+    static constexpr int ALLOC = NEED <= 32 ? 32 : (NEED <= 64 ? 64 : (NEED <= 128 ? 128 : (NEED <= 256 ? 256 : 512)));
+    static_assert(NEED <= 512, "the rings of one CTA must fit the SM's 512 tensor-memory columns");
+};
+
+template <int S, int WPC>
+__global__ void __launch_bounds__(WPC * 32, WPC == 4 ? 4 : 1)
 k_detector_tmem(const float* __restrict__ lsmooth, size_t img_px, float* __restrict__ oLx, float* __restrict__ oLy,
                 float* __restrict__ oLdet, unsigned int* __restrict__ mask, size_t mask_img_words, DetParams p, int strips_x,
                 int n_seg, int RL) {
     using G = StreamGeo<S>;
-    using RT = RingTmem<S>;
-    __shared__ float4 lq[DT_WARPS][4][32];  // cp.async queues of Lsmooth rows
-    __shared__ float4 ring_a[RT::A_IN_SMEM ? DT_WARPS : 1][RT::A_IN_SMEM ? G::D : 1][32];
+    using CFG = DetTmemCfg<S, WPC>;
+    using RT = typename CFG::RT;
+    constexpr int NSM = CFG::NSM;
+    extern __shared__ float4 det_smem[];  // [WPC][4][32] cp.async queues of Lsmooth rows, then [WPC][NSM][D][32] rings
+    float4(*lq)[4][32] = reinterpret_cast<float4(*)[4][32]>(det_smem);
+    float4(*ring_sm)[NSM > 0 ? NSM : 1][G::D][32] = reinterpret_cast<float4(*)[NSM > 0 ? NSM : 1][G::D][32]>(det_smem + WPC * 4 * 32);
     __shared__ unsigned int tmem_slot;
     const int warp = threadIdx.x >> 5;
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned int)__cvta_generic_to_shared(&tmem_slot)), "r"((unsigned int)RT::COLS) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned int)__cvta_generic_to_shared(&tmem_slot)), "r"((unsigned int)CFG::ALLOC) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int strip = blockIdx.x * DT_WARPS + warp;
+    const int strip = blockIdx.x * WPC + warp;
     if (strip < strips_x * n_seg) {  // surplus warps of the last CTA only take part in the barriers
         DetStreamCtx<S> k;
         det_stream_ctx<S>(k, p, strip % strips_x, strip / strips_x, blockIdx.z, n_seg, RL, lsmooth, img_px, oLx, oLy, oLdet, mask,
                           mask_img_words);
-        const RT rg{tmem_slot + ((unsigned int)(warp * 32) << 16), ring_a[RT::A_IN_SMEM ? warp : 0], k.lane};
+        const unsigned int tbase = tmem_slot + ((unsigned int)((warp & 3) * 32) << 16) + (unsigned int)((warp >> 2) * RT::COLS);
+        const RT rg{tbase, ring_sm[NSM > 0 ? warp : 0], k.lane};
         const int c_begin = max(k.ylo, k.Ya - 1 - 2 * S), c_end = k.Yb + 2 * S;
         if (k.has_l || k.has_r)
             det_stream_run<S, true>(k, rg, lq[warp], c_begin, c_end);
@@ -880,7 +899,12 @@ k_detector_tmem(const float* __restrict__ lsmooth, size_t img_px, float* __restr
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"((unsigned int)RT::COLS) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_slot), "r"((unsigned int)CFG::ALLOC) : "memory");
+}
+
+template <int S, int WPC>
+static size_t det_tmem_smem_bytes() {
+    return sizeof(float4) * 32 * ((size_t)WPC * 4 + (size_t)WPC * DetTmemCfg<S, WPC>::NSM * StreamGeo<S>::D);
 }
 
 // ---- bitmask -> ordered list ------------------------------------------------------------------
@@ -1000,7 +1024,22 @@ __global__ void k_scatter(const unsigned int* __restrict__ mask, const PlanDev* 
 }  // namespace
 
 // opt in to > 48 KB dynamic shared memory (call once per device, after cudaSetDevice)
+template <int S>
+static cudaError_t det_tmem_attributes() {
+    cudaError_t e = cudaFuncSetAttribute(k_detector_tmem<S, 20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)det_tmem_smem_bytes<S, 20>());
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_detector_tmem<S, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)det_tmem_smem_bytes<S, 4>());
+}
+
 cudaError_t init_detector_attributes() {
+    {
+        cudaError_t e0 = det_tmem_attributes<2>();
+        if (e0 != cudaSuccess) return e0;
+        e0 = det_tmem_attributes<3>();
+        if (e0 != cudaSuccess) return e0;
+        e0 = det_tmem_attributes<4>();
+        if (e0 != cudaSuccess) return e0;
+    }
     const int pw = DT + 2 * (2 * kMaxDetScale + 1);
     cudaError_t e = cudaFuncSetAttribute(k_detector, cudaFuncAttributeMaxDynamicSharedMemorySize, 5 * pw * pw * (int)sizeof(float));
     if (e != cudaSuccess) return e;
@@ -1082,7 +1121,14 @@ int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level)
             if (rings_in_smem)
                 k_detector_stream<S><<<dim3(sx * n_seg, 1, L.batch), 32, 0, L.stream>>>(ls, img_px, px, py, pd, mk, (size_t)P.dev.mask_words, p, sx, n_seg, RL);
             else
-                k_detector_tmem<S><<<dim3((sx * n_seg + DT_WARPS - 1) / DT_WARPS, 1, L.batch), DT_WARPS * 32, 0, L.stream>>>(ls, img_px, px, py, pd, mk, (size_t)P.dev.mask_words, p, sx, n_seg, RL);
+            {
+                // AKZ_DET_WPC=4: the four-warp CTA of round 1 (16 warps per SM); default: one 20-warp CTA per SM
+                static const int wpc = getenv("AKZ_DET_WPC") ? atoi(getenv("AKZ_DET_WPC")) : 20;
+                if (wpc == 4)
+                    k_detector_tmem<S, 4><<<dim3((sx * n_seg + 3) / 4, 1, L.batch), 4 * 32, det_tmem_smem_bytes<S, 4>(), L.stream>>>(ls, img_px, px, py, pd, mk, (size_t)P.dev.mask_words, p, sx, n_seg, RL);
+                else
+                    k_detector_tmem<S, 20><<<dim3((sx * n_seg + 19) / 20, 1, L.batch), 20 * 32, det_tmem_smem_bytes<S, 20>(), L.stream>>>(ls, img_px, px, py, pd, mk, (size_t)P.dev.mask_words, p, sx, n_seg, RL);
+            }
         };
         if (lv.s_det == 2) go(std::integral_constant<int, 2>{});
         else if (lv.s_det == 3) go(std::integral_constant<int, 3>{});
