@@ -1122,8 +1122,12 @@ int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level)
                 k_detector_stream<S><<<dim3(sx * n_seg, 1, L.batch), 32, 0, L.stream>>>(ls, img_px, px, py, pd, mk, (size_t)P.dev.mask_words, p, sx, n_seg, RL);
             else
             {
-                // AKZ_DET_WPC=4: the four-warp CTA of round 1 (16 warps per SM); default: one 20-warp CTA per SM
-                static const int wpc = getenv("AKZ_DET_WPC") ? atoi(getenv("AKZ_DET_WPC")) : 20;
+                // Default: four-warp CTAs, four per SM (16 warps). AKZ_DET_WPC=20: one 20-warp CTA per SM with the warps' ring
+                // columns packed side by side (96 registers, no spills) -- 25 % more resident warps, and measured SLOWER:
+                // detector 0.0424 -> 0.0482 ms per image (profiles/r2_ab.txt). One block per SM lives as long as its slowest
+                // of 20 warps, and for S >= 3 one or two of the five rings fall back to shared memory, the pipe the tensor-
+                // memory rings were introduced to relieve.
+                static const int wpc = getenv("AKZ_DET_WPC") ? atoi(getenv("AKZ_DET_WPC")) : 4;
                 if (wpc == 4)
                     k_detector_tmem<S, 4><<<dim3((sx * n_seg + 3) / 4, 1, L.batch), 4 * 32, det_tmem_smem_bytes<S, 4>(), L.stream>>>(ls, img_px, px, py, pd, mk, (size_t)P.dev.mask_words, p, sx, n_seg, RL);
                 else
