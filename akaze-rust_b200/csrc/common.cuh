@@ -56,8 +56,12 @@ struct PlanDev {
     int grid_shift;        // dedup hash grid: cell = 1<<grid_shift full-resolution pixels
     int grid_w, grid_h;
     int pool_cap;          // entries per class-parity pool of the single-warp cache pass (per image)
-    int lgrid_shift;       // level-pipelined cache pass: one hash grid per level in shared memory, cell = 1<<lgrid_shift px
-    int lgrid_w, lgrid_h;
+    // level-pipelined cache pass: one hash grid of u16 heads per level in shared memory; level l has cells of
+    // 1 << lgrid_shift[l] px (about twice its search radius where the budget allows), lgrid_w[l] x lgrid_h[l] of them,
+    // starting at heads[lgrid_off[l]]; lgrid_off[n_levels] = heads in total
+    int lgrid_shift[kMaxLevels];
+    int lgrid_w[kMaxLevels], lgrid_h[kMaxLevels];
+    int lgrid_off[kMaxLevels + 1];
     LevelDev lv[kMaxLevels];
 };
 

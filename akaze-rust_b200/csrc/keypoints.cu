@@ -452,7 +452,7 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
                float* __restrict__ c_y, float* __restrict__ c_resp, int* __restrict__ c_cls, unsigned int* __restrict__ n_cache,
                unsigned int* __restrict__ err_flags, unsigned char* pools, unsigned int* __restrict__ keep_flag,
                unsigned int* __restrict__ upper_done) {
-    extern __shared__ unsigned short s_heads[];  // [n_levels][lgrid cells]
+    extern __shared__ unsigned short s_heads[];  // the levels' hash grids, level l at plan->lgrid_off[l]
     __shared__ volatile int s_progress[kMaxLevels];
     __shared__ unsigned int s_appends[kMaxLevels], s_base[kMaxLevels + 1];
     __shared__ int s_ok;
@@ -462,10 +462,8 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
     const int nl = plan->n_levels;
     const unsigned int* cl = cand + (size_t)img * cand_cap;
     const unsigned int* lo = level_off + (size_t)img * (kMaxLevels + 1);
-    const int gw = plan->lgrid_w, gh = plan->lgrid_h, gshift = plan->lgrid_shift;
-    const int gcells = gw * gh;
     if (threadIdx.x == 0) s_ok = !(err_flags[img] & kErrCandOverflow) && image_fits_level_pass(plan, lo);
-    for (int i = threadIdx.x; i < nl * gcells; i += blockDim.x) s_heads[i] = kNil;
+    for (int i = threadIdx.x; i < plan->lgrid_off[nl]; i += blockDim.x) s_heads[i] = kNil;
     if (threadIdx.x < kMaxLevels) {
         s_progress[threadIdx.x] = -1;
         s_appends[threadIdx.x] = 0;
@@ -485,71 +483,96 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
     c_cls += (size_t)img * kp_cap;
 
     const LevelDev& lv = plan->lv[L];
-    unsigned short* h_cur = s_heads + (size_t)L * gcells;
-    const unsigned short* h_prv = s_heads + (size_t)(L > 0 ? L - 1 : 0) * gcells;
+    const int Lp = L > 0 ? L - 1 : 0;
+    const int gw = plan->lgrid_w[L], gh = plan->lgrid_h[L], gshift = plan->lgrid_shift[L];      // grid of this level
+    const int pgw = plan->lgrid_w[Lp], pgh = plan->lgrid_h[Lp], pshift = plan->lgrid_shift[Lp];  // grid of level L-1
+    unsigned short* h_cur = s_heads + plan->lgrid_off[L];
+    const unsigned short* h_prv = s_heads + plan->lgrid_off[Lp];
     const unsigned int beg = lo[L], end = lo[L + 1];
     const unsigned int pbeg = L > 0 ? lo[L - 1] : 0u;  // pool base of level L-1
     const float ratio = lv.ratio, size = lv.kp_size, size_sq = lv.size_sq, hr = lv.half_ratio_m1;
-    const int margin = L > 0 ? (int)ceilf(size + plan->lv[L - 1].kp_size) + (1 << gshift) + 3 : 0;
+    const int margin = L > 0 ? (int)ceilf(size + plan->lv[L - 1].kp_size) + (1 << pshift) + 3 : 0;
     const float* ldet = ldet_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
+    const unsigned int lw = (unsigned int)lv.w;
     unsigned int n_app = 0;  // appends of this level (uniform across the warp)
     unsigned int cnt = 0;    // pool entries of this level (appends + replacements)
 
-    unsigned int nx_flat = 0;
+    // the 32 candidates of a batch, one per lane: position in the level, response
+    int nx_px = 0, nx_py = 0;
     float nx_resp = 0.0f;
     if (beg + lane < end) {
-        nx_flat = cl[beg + lane];
-        nx_resp = fabsf(ldet[nx_flat]);  // scale_space_extrema.rs:44
+        const unsigned int f = cl[beg + lane];
+        nx_py = (int)(f / lw);
+        nx_px = (int)(f - (unsigned int)nx_py * lw);
+        nx_resp = fabsf(ldet[f]);  // scale_space_extrema.rs:44
     }
     constexpr int GL = 32 / KG;  // lanes per candidate
     const int grp = lane / GL, sub = lane % GL;
     const bool leader = sub == 0;
+#ifdef AKZ_DEDUP_STATS
+    long long t_wait = 0, t_search = 0, t_conf = 0, t_commit = 0, t_all0 = clock64();
+    unsigned int n_steps = 0, n_hops = 0, n_cells = 0;
+#define DSTAT(x) x
+#else
+#define DSTAT(x)
+#endif
+    // Both pools are filled in raster order of the level that owns them, so along a cell's list (newest entry first) y never
+    // grows: once an entry lies more than size (+1 for rounding) above the candidate, the rest of the list does too.
+    const float y_cut = size + 1.0f;
     for (unsigned int base = beg; base < end; base += 32) {
-        const unsigned int my_flat = nx_flat;
+        const int my_px = nx_px, my_py = nx_py;
         const float my_resp = nx_resp;
         if (base + 32 + lane < end) {
-            nx_flat = cl[base + 32 + lane];
-            nx_resp = fabsf(ldet[nx_flat]);
+            const unsigned int f = cl[base + 32 + lane];
+            nx_py = (int)(f / lw);
+            nx_px = (int)(f - (unsigned int)nx_py * lw);
+            nx_resp = fabsf(ldet[f]);
         }
         const int n_here = min(32u, end - base);
         int k0 = 0;
         while (k0 < n_here) {
             // publish the row of the first undecided candidate; wait until level L-1 is `margin` rows past this step's last
+            DSTAT(long long t0 = clock64(); n_steps++;)
             {
-                const unsigned int f0 = __shfl_sync(FULL, my_flat, k0);
-                if (lane == 0) s_progress[L] = (int)((float)(f0 / (unsigned int)lv.w) * ratio);
+                const int r0 = __shfl_sync(FULL, my_py, k0);
+                if (lane == 0) s_progress[L] = (int)((float)r0 * ratio);
                 if (L > 0) {
-                    const unsigned int fl = __shfl_sync(FULL, my_flat, min(k0 + KG - 1, n_here - 1));
-                    const int need = (int)((float)(fl / (unsigned int)lv.w) * ratio) + margin;
-                    while (s_progress[L - 1] < need) __nanosleep(100);
+                    const int rl = __shfl_sync(FULL, my_py, min(k0 + KG - 1, n_here - 1));
+                    const int need = (int)((float)rl * ratio) + margin;
+                    while (s_progress[L - 1] < need) __nanosleep(40);
                     __threadfence_block();
                 }
             }
+            DSTAT(long long t1 = clock64(); t_wait += t1 - t0;)
             const int k = k0 + grp;
             const bool active = k < n_here;
-            const unsigned int flat = __shfl_sync(FULL, my_flat, k & 31);
+            const int px = __shfl_sync(FULL, my_px, k & 31), py = __shfl_sync(FULL, my_py, k & 31);
             const float resp = __shfl_sync(FULL, my_resp, k & 31);
-            const int px = (int)(flat % (unsigned int)lv.w), py = (int)(flat / (unsigned int)lv.w);
             const float qx = (float)px * ratio, qy = (float)py * ratio;  // :62-65 compares the level point * ratio
             unsigned int best = kDeadKey;  // lowest matching key (= lowest slot)
             unsigned int best_ref = 0;     // (1 if in the pool of level L-1) << 16 | pool index
             if (active) {
-                const int cx0 = max(0, ((int)floorf(qx - size) - 1) >> gshift);
-                const int cx1 = min(gw - 1, ((int)floorf(qx + size) + 1) >> gshift);
-                const int cy0 = max(0, ((int)floorf(qy - size) - 1) >> gshift);
-                const int cy1 = min(gh - 1, ((int)floorf(qy + size) + 1) >> gshift);
+                const int x_lo = (int)floorf(qx - size) - 1, x_hi = (int)floorf(qx + size) + 1;
+                const int y_lo = (int)floorf(qy - size) - 1, y_hi = (int)floorf(qy + size) + 1;
+                const int cx0 = max(0, x_lo >> gshift), cx1 = min(gw - 1, x_hi >> gshift);
+                const int cy0 = max(0, y_lo >> gshift), cy1 = min(gh - 1, y_hi >> gshift);
                 const int nx = cx1 - cx0 + 1;
                 const int ncell = nx * (cy1 - cy0 + 1);
-                const int ntot = (L > 0) ? 2 * ncell : ncell;
+                const int qx0 = max(0, x_lo >> pshift), qx1 = min(pgw - 1, x_hi >> pshift);
+                const int qy0 = max(0, y_lo >> pshift), qy1 = min(pgh - 1, y_hi >> pshift);
+                const int pnx = qx1 - qx0 + 1;
+                const int ntot = (L > 0) ? ncell + pnx * (qy1 - qy0 + 1) : ncell;
                 for (int c = sub; c < ntot; c += GL) {
                     const bool prev = c >= ncell;
                     const int cc = prev ? c - ncell : c;
-                    const int cell = (cy0 + cc / nx) * gw + (cx0 + cc % nx);
                     const unsigned int eb = prev ? pbeg : beg;
-                    unsigned short e = prev ? h_prv[cell] : h_cur[cell];
+                    unsigned short e = prev ? h_prv[(qy0 + cc / pnx) * pgw + (qx0 + cc % pnx)] : h_cur[(cy0 + cc / nx) * gw + (cx0 + cc % nx)];
+                    DSTAT(n_cells++;)
                     while (e != kNil) {
+                        DSTAT(n_hops++;)
                         const unsigned int at = eb + e;
                         const float dx = qx - P.x[at], dy = qy - P.y[at];
+                        if (dy > y_cut) break;
                         const float dist = dx * dx + dy * dy;
                         const unsigned int key = P.key[at];  // kDeadKey = replaced entry: never < best
                         if (dist <= size_sq && key < best) {
@@ -579,18 +602,26 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
             // conflict rule of k_dedup_smem: an earlier candidate a of this step that writes changes b's decision only if
             // its new entry lies within `size` of b, or it replaces the very slot b matched
             bool conflict = false;
-#pragma unroll
-            for (int a = 0; a < KG - 1; a++) {
-                const int a_act = __shfl_sync(FULL, act, a * GL);
-                const float a_fx = __shfl_sync(FULL, fx, a * GL), a_fy = __shfl_sync(FULL, fy, a * GL);
-                const unsigned int a_best = __shfl_sync(FULL, best, a * GL);
-                if (a < grp && a_act != 0 && active) {
-                    const float dx = qx - a_fx, dy = qy - a_fy;
-                    const float dist = dx * dx + dy * dy;
-                    if (dist <= size_sq || (a_act == 2 && a_best == best)) conflict = true;
+            DSTAT(__syncwarp(); long long t2 = clock64(); t_search += t2 - t1;)
+            {
+                const unsigned int wr = __ballot_sync(FULL, leader && act != 0);  // leaders of the candidates that write
+                unsigned int earlier = wr & ((1u << (grp * GL)) - 1u);
+                while (__any_sync(FULL, earlier != 0)) {
+                    // every lane looks at its own next earlier writer (the lists differ only in length)
+                    const int src = earlier ? __ffs(earlier) - 1 : 0;
+                    const int a_act = __shfl_sync(FULL, act, src);
+                    const float a_fx = __shfl_sync(FULL, fx, src), a_fy = __shfl_sync(FULL, fy, src);
+                    const unsigned int a_best = __shfl_sync(FULL, best, src);
+                    if (earlier && active) {
+                        const float dx = qx - a_fx, dy = qy - a_fy;
+                        const float dist = dx * dx + dy * dy;
+                        if (dist <= size_sq || (a_act == 2 && a_best == best)) conflict = true;
+                    }
+                    earlier &= earlier - 1;
                 }
             }
             const unsigned int cmask = __ballot_sync(FULL, conflict && leader);
+            DSTAT(long long t3 = clock64(); t_conf += t3 - t2;)
             const int n_act = min(KG, n_here - k0);
             const int n_commit = cmask ? min(n_act, (__ffs(cmask) - 1) / GL) : n_act;  // >= 1: group 0 never conflicts
             const bool commits = leader && grp < n_commit;
@@ -625,8 +656,17 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
             k0 += n_commit;
             __syncwarp();
             __threadfence_block();  // this step's entries and links are visible before the progress moves on
+            DSTAT(t_commit += clock64() - t3;)
         }
     }
+#ifdef AKZ_DEDUP_STATS
+    {
+        const unsigned int hops = __reduce_add_sync(FULL, n_hops), cells = __reduce_add_sync(FULL, n_cells);
+        if (img == 0 && lane == 0)
+            printf("L%2d cand %6u steps %5u appends %5u entries %5u cells %7u hops %7u | kcycles total %7lld wait %7lld search %7lld conflict %6lld commit %6lld\n", L,
+                   end - beg, n_steps, n_app, cnt, cells, hops, (clock64() - t_all0) / 1000, t_wait / 1000, t_search / 1000, t_conf / 1000, t_commit / 1000);
+    }
+#endif
     __threadfence_block();
     if (lane == 0) {
         s_appends[L] = n_app;
@@ -657,8 +697,10 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
     // becomes a look into at most a handful of cells.
     keep_flag += (size_t)img * kp_cap;
     const bool has_up = L + 1 < nl;
-    const unsigned short* h_up = s_heads + (size_t)(has_up ? L + 1 : L) * gcells;
-    const unsigned int ubeg = lo[has_up ? L + 1 : L];
+    const int Lu = has_up ? L + 1 : L;
+    const unsigned short* h_up = s_heads + plan->lgrid_off[Lu];
+    const int ugw = plan->lgrid_w[Lu], ugh = plan->lgrid_h[Lu], ushift = plan->lgrid_shift[Lu];
+    const unsigned int ubeg = lo[Lu];
     constexpr unsigned int kIdxMask = (1u << kKeyShift) - 1u;
     for (unsigned int e = lane; e < cnt; e += 32) {
         const unsigned int at = beg + e;
@@ -668,11 +710,11 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
         const float xi = P.x[at], yi = P.y[at];
         bool repeated = false;
         if (has_up) {
-            const int cx0 = max(0, ((int)floorf(xi - size) - 1) >> gshift), cx1 = min(gw - 1, ((int)floorf(xi + size) + 1) >> gshift);
-            const int cy0 = max(0, ((int)floorf(yi - size) - 1) >> gshift), cy1 = min(gh - 1, ((int)floorf(yi + size) + 1) >> gshift);
+            const int cx0 = max(0, ((int)floorf(xi - size) - 1) >> ushift), cx1 = min(ugw - 1, ((int)floorf(xi + size) + 1) >> ushift);
+            const int cy0 = max(0, ((int)floorf(yi - size) - 1) >> ushift), cy1 = min(ugh - 1, ((int)floorf(yi + size) + 1) >> ushift);
             for (int cy = cy0; cy <= cy1 && !repeated; cy++)
                 for (int cx = cx0; cx <= cx1 && !repeated; cx++) {
-                    unsigned short u = h_up[cy * gw + cx];
+                    unsigned short u = h_up[cy * ugw + cx];
                     while (u != kNil) {
                         const unsigned int ua = ubeg + u;
                         const unsigned int ukey = P.key[ua];
@@ -1133,17 +1175,22 @@ k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plan
 
 }  // namespace
 
-cudaError_t init_keypoint_attributes() {
+template <int KG>
+static cudaError_t level_pass_attributes() {
     // see init_detector_attributes: the cache pass must not pin a small shared-memory carveout on the SMs it lives on
-    cudaError_t e = cudaFuncSetAttribute(k_dedup_levels<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_dedup_levels<KG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess || getenv("AKZ_NO_CARVEOUT") != nullptr) return e;
+    return cudaFuncSetAttribute(k_dedup_levels<KG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+cudaError_t init_keypoint_attributes() {
+    cudaError_t e = level_pass_attributes<8>();
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_dedup_levels<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    e = level_pass_attributes<16>();
+    if (e != cudaSuccess) return e;
+    e = level_pass_attributes<32>();
     if (e != cudaSuccess) return e;
     if (getenv("AKZ_NO_CARVEOUT") != nullptr) return cudaSuccess;
-    e = cudaFuncSetAttribute(k_dedup_levels<8>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_dedup_levels<16>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_dedup_smem, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_dedup, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1151,22 +1198,27 @@ cudaError_t init_keypoint_attributes() {
 
 size_t dedup_pool_bytes(const Plan& P) { return (size_t)P.dev.pool_cap * kPoolBytesPerEntry; }
 size_t dedup_level_pool_bytes(uint32_t cand_cap) { return (size_t)cand_cap * kLevelPoolBytesPerCand; }
-static size_t level_pass_smem(const Plan& P) { return (size_t)P.dev.n_levels * P.dev.lgrid_w * P.dev.lgrid_h * sizeof(unsigned short); }
+static size_t level_pass_smem(const Plan& P) { return (size_t)P.dev.lgrid_off[P.dev.n_levels] * sizeof(unsigned short); }
+
+template <int KG>
+static void launch_level_pass(const Launch& L, const Plan& P, const Buffers& B, size_t smem) {
+    k_dedup_levels<KG><<<L.batch, 32 * P.dev.n_levels, smem, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap,
+                                                                         L.kp_cap, B.c_x, B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags,
+                                                                         B.level_pool, B.keep_flag, B.upper_done);
+}
 
 int launch_dedup(const Launch& L, const Plan& P, const Buffers& B) {
     // every image is handled by exactly one of the two kernels launched here (image_fits_*_pass)
     static const bool single_warp = getenv("AKZ_DEDUP_SINGLE") != nullptr;  // A/B switch: the one-warp-per-image pass
     const size_t smem = level_pass_smem(P);
     const bool levels = !single_warp && smem <= 200 * 1024;
-    static const int groups = getenv("AKZ_DEDUP_GROUPS") ? atoi(getenv("AKZ_DEDUP_GROUPS")) : 8;  // A/B switch
-    if (levels && groups == 16) {
-        k_dedup_levels<16><<<L.batch, 32 * P.dev.n_levels, smem, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap,
-                                                                            L.kp_cap, B.c_x, B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags,
-                                                                            B.level_pool, B.keep_flag, B.upper_done);
+    static const int groups = getenv("AKZ_DEDUP_GROUPS") ? atoi(getenv("AKZ_DEDUP_GROUPS")) : 8;  // A/B switch: candidates per step
+    if (levels && groups == 32) {
+        launch_level_pass<32>(L, P, B, smem);
+    } else if (levels && groups == 16) {
+        launch_level_pass<16>(L, P, B, smem);
     } else if (levels) {
-        k_dedup_levels<8><<<L.batch, 32 * P.dev.n_levels, smem, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap,
-                                                                           L.kp_cap, B.c_x, B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags,
-                                                                           B.level_pool, B.keep_flag, B.upper_done);
+        launch_level_pass<8>(L, P, B, smem);
     } else {
         k_dedup_smem<<<L.batch, 32, 0, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap, L.kp_cap, B.c_x,
                                                    B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags, B.dedup_pool, B.upper_done);
