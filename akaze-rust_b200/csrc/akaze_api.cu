@@ -267,34 +267,9 @@ std::string build_plan(uint32_t w, uint32_t h, const akz_config& cfg, Plan* P) {
     // cache-pass pools: room for the candidates of the busiest level (a photo-like 1080p frame has ~2 k per level, a
     // 3840x2160 one ~10 k); images beyond it take the global-memory pass
     D.pool_cap = (int)std::min<uint64_t>(64512, std::max<uint64_t>(4096, (((uint64_t)w * h / 384) + 1023) & ~1023ull));
-    // level-pipelined cache pass: u16 heads of one grid per level in shared memory. A level's lookups reach kp_size
-    // around a point, so cells of about twice that keep a lookup at one to four cells with an entry or two each; the
-    // full-resolution levels cannot afford that (8 px cells of a 1080p frame are 65 KB per level), so the grids are coarsened,
-    // largest first (ties: the level with the fewest candidates, i.e. the highest), until all of them fit the budget.
-    {
-        static const int budget_kb = getenv("AKZ_DEDUP_SMEM_KB") ? atoi(getenv("AKZ_DEDUP_SMEM_KB")) : 144;
-        auto cells = [&](int l) { return (size_t)(((int)w >> D.lgrid_shift[l]) + 1) * (((int)h >> D.lgrid_shift[l]) + 1); };
-        for (int l = 0; l < nl; l++) {
-            D.lgrid_shift[l] = 3;
-            while ((float)(1 << D.lgrid_shift[l]) < 2.0f * D.lv[l].kp_size) D.lgrid_shift[l]++;
-        }
-        for (;;) {
-            size_t total = 0;
-            int worst = 0;
-            for (int l = 0; l < nl; l++) {
-                total += cells(l);
-                if (cells(l) >= cells(worst)) worst = l;
-            }
-            if (total * 2 <= (size_t)budget_kb * 1024 || cells(worst) <= 4) break;
-            D.lgrid_shift[worst]++;
-        }
-        D.lgrid_off[0] = 0;
-        for (int l = 0; l < nl; l++) {
-            D.lgrid_w[l] = ((int)w >> D.lgrid_shift[l]) + 1;
-            D.lgrid_h[l] = ((int)h >> D.lgrid_shift[l]) + 1;
-            D.lgrid_off[l + 1] = D.lgrid_off[l] + D.lgrid_w[l] * D.lgrid_h[l];
-        }
-    }
+    // level-pipelined cache pass: one row table per level in shared memory (a 1080p frame: 16 KB, 3840x2160: 32 KB)
+    D.ltab_off[0] = 0;
+    for (int l = 0; l < nl; l++) D.ltab_off[l + 1] = D.ltab_off[l] + ((D.lv[l].h + 2 + 7) & ~7);
     return "";
 }
 

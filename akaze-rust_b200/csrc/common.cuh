@@ -56,12 +56,9 @@ struct PlanDev {
     int grid_shift;        // dedup hash grid: cell = 1<<grid_shift full-resolution pixels
     int grid_w, grid_h;
     int pool_cap;          // entries per class-parity pool of the single-warp cache pass (per image)
-    // level-pipelined cache pass: one hash grid of u16 heads per level in shared memory; level l has cells of
-    // 1 << lgrid_shift[l] px (about twice its search radius where the budget allows), lgrid_w[l] x lgrid_h[l] of them,
-    // starting at heads[lgrid_off[l]]; lgrid_off[n_levels] = heads in total
-    int lgrid_shift[kMaxLevels];
-    int lgrid_w[kMaxLevels], lgrid_h[kMaxLevels];
-    int lgrid_off[kMaxLevels + 1];
+    // level-pipelined cache pass: one row table of u16 pool indices per level in shared memory, level l (lv[l].h + 2
+    // entries) at ltab_off[l]; ltab_off[n_levels] = entries in total
+    int ltab_off[kMaxLevels + 1];
     LevelDev lv[kMaxLevels];
 };
 

@@ -406,24 +406,29 @@ k_dedup_smem(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ 
 // The sequential pass visits the levels one after the other, but a level-L candidate at full-resolution row Y only ever
 // reads or changes cache entries of classes L and L-1 that lie within size_L of it. So level L may run concurrently with
 // level L-1 as long as it stays far enough BEHIND it: when the level L-1 warp works on the candidate at row P, everything
-// it will still touch lies at rows >= P - size_{L-1} - 2 (lookups, replacements) or in hash cells at rows >= P (inserts),
-// and the level-L warp at row Y touches rows <= Y + size_L + 2. With
-//     P >= Y + size_L + size_{L-1} + cell + 3
-// the two never meet (rows AND hash-cell rows are disjoint), hence level L sees exactly the state the sequential pass
-// would show it: every level-(L-1) decision that can influence it has been taken, none of its own writes can influence a
-// pending level-(L-1) decision. Each warp publishes the row of its first undecided candidate (s_progress), its follower
-// spins on it. Within a warp the pass is k_dedup_smem's (eight speculative candidates per step, exact conflict rule).
+// it will still use or change lies at rows >= P - size_{L-1}, and the level-L warp at row Y uses rows <= Y + size_L. With
+//     P >= Y + size_L + size_{L-1} + 4 * ratio_{L-1} + 6
+// the two never meet, hence level L sees exactly the state the sequential pass would show it: every level-(L-1) decision
+// that can influence it has been taken, none of its own writes can influence a pending level-(L-1) decision. Each warp
+// publishes the row of its first undecided candidate (s_progress), its follower spins on it. Within a warp the pass is
+// k_dedup_smem's (KG speculative candidates per step, exact conflict rule).
 //
 // Slots: the sequential pass numbers cache slots in append order = (level, running index inside the level). That pair is
 // the KEY of an entry (a replacement keeps the key of the slot it takes over), "lowest slot first" is "lowest key first",
 // and the final slot numbers are the keys compacted by a prefix sum over the levels' append counts once all warps are
-// through. Entries live in per-level pools (class L = created by warp L: appended or replaced into), each with its own
-// hash grid of u16 heads in shared memory; a level-L candidate searches the grids of L and L-1.
-// 20 k candidates of a 1080p frame: 16 warps take ~1/6 of the time the single warp took.
+// through.
+//
+// Pools: entries live in per-level pools (class L = written by warp L: appended or replaced into). A warp walks its
+// candidates in raster order, so its pool is SORTED BY ROW as it grows; a table in shared memory holds, for every row of the
+// level, the index of the first entry at or below it. "All entries within size of a point" is then one contiguous index
+// range of the pool (the rows the circle touches, all columns): 16-byte records, independent loads, no lists to chase.
+// The first version hashed the entries into cell lists; chasing them cost two dependent L2 round trips per hop (stores do
+// not allocate in L1, so freshly written entries always miss) and left a step of eight candidates at 4.4 k cycles:
+// 0.94 ms for a 1080p frame, 4.2 ms for a 3840x2160 one. Row ranges: see profiles/README.md.
 // ------------------------------------------------------------------------------------------------
 constexpr unsigned int kDeadKey = 0xffffffffu;
 constexpr int kKeyShift = 20;               // key = (level of the append << 20) | index of the append inside its level
-constexpr unsigned int kMaxLevelCands = 65534;  // pool indices are u16
+constexpr unsigned int kMaxLevelCands = 65534;  // row tables hold u16 indices
 
 __device__ __forceinline__ bool image_fits_level_pass(const PlanDev* plan, const unsigned int* lo) {
     for (int l = 0; l < plan->n_levels; l++)
@@ -431,28 +436,18 @@ __device__ __forceinline__ bool image_fits_level_pass(const PlanDev* plan, const
     return true;
 }
 
-struct LevelPools {  // per image: entry e of level L sits at index lo[L] + e of every array (cand_cap entries each)
-    float *x, *y, *resp;
-    unsigned int* key;
-    unsigned short* next;
-    __device__ __forceinline__ LevelPools(unsigned char* slab, unsigned int cap) {
-        x = reinterpret_cast<float*>(slab);
-        y = x + cap;
-        resp = y + cap;
-        key = reinterpret_cast<unsigned int*>(resp + cap);
-        next = reinterpret_cast<unsigned short*>(key + cap);
-    }
-};
-constexpr size_t kLevelPoolBytesPerCand = 4 * 4 + 2;
+// one pool entry: the point as :89-92 stores it (x, y), |response|, key -- 16 bytes, one load.
+// Entry e of level l sits at index lo[l] + e of the image's slab (cand_cap entries).
+constexpr size_t kLevelPoolBytesPerCand = sizeof(uint4);
 
-template <int KG>  // candidates decided per step (32 / KG lanes each)
-__global__ void __launch_bounds__(1024)
+template <int KG, int MAXT>  // candidates decided per step (32 / KG lanes each); threads per block (32 per level)
+__global__ void __launch_bounds__(MAXT)
 k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ cand, const unsigned int* __restrict__ level_off,
                const float* __restrict__ ldet_plane, int batch, unsigned int cand_cap, unsigned int kp_cap, float* __restrict__ c_x,
                float* __restrict__ c_y, float* __restrict__ c_resp, int* __restrict__ c_cls, unsigned int* __restrict__ n_cache,
                unsigned int* __restrict__ err_flags, unsigned char* pools, unsigned int* __restrict__ keep_flag,
                unsigned int* __restrict__ upper_done) {
-    extern __shared__ unsigned short s_heads[];  // the levels' hash grids, level l at plan->lgrid_off[l]
+    extern __shared__ uint4 s_dyn[];  // per level KG step records (float4), then the row tables (u16, level l at ltab_off[l])
     __shared__ volatile int s_progress[kMaxLevels];
     __shared__ unsigned int s_appends[kMaxLevels], s_base[kMaxLevels + 1];
     __shared__ int s_ok;
@@ -460,23 +455,24 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
     const int img = blockIdx.x;
     const int lane = threadIdx.x & 31, L = threadIdx.x >> 5;  // one warp per level
     const int nl = plan->n_levels;
+    float4* s_step = reinterpret_cast<float4*>(s_dyn) + L * KG;
+    unsigned short* s_rows = reinterpret_cast<unsigned short*>(s_dyn + nl * KG);
     const unsigned int* cl = cand + (size_t)img * cand_cap;
     const unsigned int* lo = level_off + (size_t)img * (kMaxLevels + 1);
     if (threadIdx.x == 0) s_ok = !(err_flags[img] & kErrCandOverflow) && image_fits_level_pass(plan, lo);
-    for (int i = threadIdx.x; i < plan->lgrid_off[nl]; i += blockDim.x) s_heads[i] = kNil;
     if (threadIdx.x < kMaxLevels) {
         s_progress[threadIdx.x] = -1;
         s_appends[threadIdx.x] = 0;
     }
     __syncthreads();
-    if (!s_ok) {  // candidate overflow: nothing to do; a level beyond the u16 pools: k_dedup takes the image
+    if (!s_ok) {  // candidate overflow: nothing to do; a level beyond the u16 tables: k_dedup takes the image
         if (threadIdx.x == 0 && (err_flags[img] & kErrCandOverflow)) {
             n_cache[img] = 0;
             upper_done[img] = 0;
         }
         return;
     }
-    const LevelPools P(pools + (size_t)img * ((size_t)cand_cap * kLevelPoolBytesPerCand), cand_cap);
+    float4* pool = reinterpret_cast<float4*>(pools + (size_t)img * ((size_t)cand_cap * kLevelPoolBytesPerCand));
     c_x += (size_t)img * kp_cap;
     c_y += (size_t)img * kp_cap;
     c_resp += (size_t)img * kp_cap;
@@ -484,18 +480,22 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
 
     const LevelDev& lv = plan->lv[L];
     const int Lp = L > 0 ? L - 1 : 0;
-    const int gw = plan->lgrid_w[L], gh = plan->lgrid_h[L], gshift = plan->lgrid_shift[L];      // grid of this level
-    const int pgw = plan->lgrid_w[Lp], pgh = plan->lgrid_h[Lp], pshift = plan->lgrid_shift[Lp];  // grid of level L-1
-    unsigned short* h_cur = s_heads + plan->lgrid_off[L];
-    const unsigned short* h_prv = s_heads + plan->lgrid_off[Lp];
+    const LevelDev& pv = plan->lv[Lp];
+    unsigned short* t_cur = s_rows + plan->ltab_off[L];        // t_cur[r] = entries of this pool above row r
+    const unsigned short* t_prv = s_rows + plan->ltab_off[Lp];
     const unsigned int beg = lo[L], end = lo[L + 1];
     const unsigned int pbeg = L > 0 ? lo[L - 1] : 0u;  // pool base of level L-1
     const float ratio = lv.ratio, size = lv.kp_size, size_sq = lv.size_sq, hr = lv.half_ratio_m1;
-    const int margin = L > 0 ? (int)ceilf(size + plan->lv[L - 1].kp_size) + (1 << pshift) + 3 : 0;
+    const float inv_ratio = 1.0f / ratio, p_ratio = pv.ratio, p_hr = pv.half_ratio_m1, p_inv = 1.0f / pv.ratio;
+    const int p_rows = pv.h;
+    const int margin = L > 0 ? (int)ceilf(size + pv.kp_size) + 4 * (int)p_ratio + 6 : 0;
     const float* ldet = ldet_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
     const unsigned int lw = (unsigned int)lv.w;
     unsigned int n_app = 0;  // appends of this level (uniform across the warp)
     unsigned int cnt = 0;    // pool entries of this level (appends + replacements)
+    int filled = 0;          // t_cur[0 .. filled] are final
+    int seen = -1;           // the last progress of level L-1 this warp has read
+    if (lane == 0) t_cur[0] = 0;
 
     // the 32 candidates of a batch, one per lane: position in the level, response
     int nx_px = 0, nx_py = 0;
@@ -509,16 +509,14 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
     constexpr int GL = 32 / KG;  // lanes per candidate
     const int grp = lane / GL, sub = lane % GL;
     const bool leader = sub == 0;
+    const unsigned int lt = (1u << lane) - 1u;
 #ifdef AKZ_DEDUP_STATS
     long long t_wait = 0, t_search = 0, t_conf = 0, t_commit = 0, t_all0 = clock64();
-    unsigned int n_steps = 0, n_hops = 0, n_cells = 0;
+    unsigned int n_steps = 0, n_scanned = 0;
 #define DSTAT(x) x
 #else
 #define DSTAT(x)
 #endif
-    // Both pools are filled in raster order of the level that owns them, so along a cell's list (newest entry first) y never
-    // grows: once an entry lies more than size (+1 for rounding) above the candidate, the rest of the list does too.
-    const float y_cut = size + 1.0f;
     for (unsigned int base = beg; base < end; base += 32) {
         const int my_px = nx_px, my_py = nx_py;
         const float my_resp = nx_resp;
@@ -531,18 +529,23 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
         const int n_here = min(32u, end - base);
         int k0 = 0;
         while (k0 < n_here) {
-            // publish the row of the first undecided candidate; wait until level L-1 is `margin` rows past this step's last
             DSTAT(long long t0 = clock64(); n_steps++;)
-            {
-                const int r0 = __shfl_sync(FULL, my_py, k0);
-                if (lane == 0) s_progress[L] = (int)((float)r0 * ratio);
-                if (L > 0) {
-                    const int rl = __shfl_sync(FULL, my_py, min(k0 + KG - 1, n_here - 1));
-                    const int need = (int)((float)rl * ratio) + margin;
-                    while (s_progress[L - 1] < need) __nanosleep(40);
+            // Rows up to the first undecided candidate's are complete: close their table entries (published below, once the
+            // search has given the last steps' pool writes time to land); wait until level L-1 is `margin` rows past this
+            // step's last candidate.
+            const int r0 = __shfl_sync(FULL, my_py, k0);
+#pragma unroll 1
+            for (int r = filled + 1 + lane; r <= r0; r += 32) t_cur[r] = (unsigned short)cnt;
+            filled = r0;
+            if (L > 0) {
+                const int rl = __shfl_sync(FULL, my_py, min(k0 + KG - 1, n_here - 1));
+                const int need = (int)((float)rl * ratio) + margin;
+                if (seen < need) {  // (a value seen earlier was followed by a fence then: everything up to it is visible)
+                    while ((seen = s_progress[L - 1]) < need) __nanosleep(20);
                     __threadfence_block();
                 }
             }
+            __syncwarp();
             DSTAT(long long t1 = clock64(); t_wait += t1 - t0;)
             const int k = k0 + grp;
             const bool active = k < n_here;
@@ -550,123 +553,122 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
             const float resp = __shfl_sync(FULL, my_resp, k & 31);
             const float qx = (float)px * ratio, qy = (float)py * ratio;  // :62-65 compares the level point * ratio
             unsigned int best = kDeadKey;  // lowest matching key (= lowest slot)
-            unsigned int best_ref = 0;     // (1 if in the pool of level L-1) << 16 | pool index
+            unsigned int best_at = 0;      // its index in the slab
+            float best_resp = 0.0f;
             if (active) {
-                const int x_lo = (int)floorf(qx - size) - 1, x_hi = (int)floorf(qx + size) + 1;
-                const int y_lo = (int)floorf(qy - size) - 1, y_hi = (int)floorf(qy + size) + 1;
-                const int cx0 = max(0, x_lo >> gshift), cx1 = min(gw - 1, x_hi >> gshift);
-                const int cy0 = max(0, y_lo >> gshift), cy1 = min(gh - 1, y_hi >> gshift);
-                const int nx = cx1 - cx0 + 1;
-                const int ncell = nx * (cy1 - cy0 + 1);
-                const int qx0 = max(0, x_lo >> pshift), qx1 = min(pgw - 1, x_hi >> pshift);
-                const int qy0 = max(0, y_lo >> pshift), qy1 = min(pgh - 1, y_hi >> pshift);
-                const int pnx = qx1 - qx0 + 1;
-                const int ntot = (L > 0) ? ncell + pnx * (qy1 - qy0 + 1) : ncell;
-                for (int c = sub; c < ntot; c += GL) {
-                    const bool prev = c >= ncell;
-                    const int cc = prev ? c - ncell : c;
-                    const unsigned int eb = prev ? pbeg : beg;
-                    unsigned short e = prev ? h_prv[(qy0 + cc / pnx) * pgw + (qx0 + cc % pnx)] : h_cur[(cy0 + cc / nx) * gw + (cx0 + cc % nx)];
-                    DSTAT(n_cells++;)
-                    while (e != kNil) {
-                        DSTAT(n_hops++;)
-                        const unsigned int at = eb + e;
-                        const float dx = qx - P.x[at], dy = qy - P.y[at];
-                        if (dy > y_cut) break;
+                // this level's entries from the first row the circle can touch (not past the rows closed above) to the newest,
+                // then the rows of level L-1 it can touch; one index space, eight independent loads in flight per lane
+                const int r_lo = max(0, min(r0, (int)floorf((qy - size - hr) * inv_ratio) - 1));
+                const unsigned int i0 = beg + t_cur[r_lo];
+                const unsigned int n_cur = beg + cnt - i0;
+                unsigned int j0 = 0, n_tot = n_cur;
+                if (L > 0) {
+                    const int p_lo = max(0, (int)floorf((qy - size - p_hr) * p_inv) - 1);
+                    const int p_hi = min(p_rows - 1, (int)ceilf((qy + size - p_hr) * p_inv) + 1);
+                    if (p_lo <= p_hi) {
+                        j0 = pbeg + t_prv[p_lo];
+                        n_tot += pbeg + t_prv[p_hi + 1] - j0;
+                    }
+                }
+                const unsigned int j_off = j0 - n_cur;  // index t >= n_cur of the joint space is entry j0 + (t - n_cur)
+                constexpr int UN = 8;
+#pragma unroll 1
+                for (unsigned int t = sub; t < n_tot; t += UN * GL) {
+                    float4 rec[UN];
+                    unsigned int at[UN];
+#pragma unroll
+                    for (int u = 0; u < UN; u++) {
+                        const unsigned int idx = min(t + u * GL, n_tot - 1u);  // past the end: the last entry once more
+                        at[u] = idx + (idx < n_cur ? i0 : j_off);
+                        rec[u] = pool[at[u]];
+                    }
+#pragma unroll
+                    for (int u = 0; u < UN; u++) {
+                        const float dx = qx - rec[u].x, dy = qy - rec[u].y;
                         const float dist = dx * dx + dy * dy;
-                        const unsigned int key = P.key[at];  // kDeadKey = replaced entry: never < best
-                        if (dist <= size_sq && key < best) {
+                        const unsigned int key = __float_as_uint(rec[u].w);
+                        DSTAT(n_scanned++;)
+                        if (dist <= size_sq && key < best) {  // kDeadKey = replaced entry: never < best
                             best = key;
-                            best_ref = ((prev ? 1u : 0u) << 16) | e;
+                            best_at = at[u];
+                            best_resp = rec[u].z;
                         }
-                        e = P.next[at];
                     }
                 }
             }
 #pragma unroll
             for (int o = 1; o < GL; o <<= 1) {
                 const unsigned int ob = __shfl_xor_sync(FULL, best, o);
-                const unsigned int orf = __shfl_xor_sync(FULL, best_ref, o);
+                const unsigned int oa = __shfl_xor_sync(FULL, best_at, o);
+                const float orr = __shfl_xor_sync(FULL, best_resp, o);
                 if (ob < best) {
                     best = ob;
-                    best_ref = orf;
+                    best_at = oa;
+                    best_resp = orr;
                 }
             }
-            const unsigned int b_at = ((best_ref >> 16) ? pbeg : beg) + (best_ref & 0xffffu);
             int act = 0;  // 0 = drop, 1 = append, 2 = replace the entry holding key `best`
             if (active) {
                 if (best == kDeadKey) act = 1;
-                else if (resp > P.resp[b_at]) act = 2;  // :67
+                else if (resp > best_resp) act = 2;  // :67
             }
             const float fx = (float)px * ratio + hr, fy = (float)py * ratio + hr;  // :89-92
+            DSTAT(__syncwarp(); long long t2 = clock64(); t_search += t2 - t1;)
             // conflict rule of k_dedup_smem: an earlier candidate a of this step that writes changes b's decision only if
             // its new entry lies within `size` of b, or it replaces the very slot b matched
+            if (leader) s_step[grp] = make_float4(fx, fy, __int_as_float(act), __uint_as_float(best));
+            __threadfence_block();  // the table rows closed above and every earlier step's pool writes, then the row
+            if (lane == 0) s_progress[L] = (int)((float)r0 * ratio);
+            __syncwarp();
             bool conflict = false;
-            DSTAT(__syncwarp(); long long t2 = clock64(); t_search += t2 - t1;)
-            {
-                const unsigned int wr = __ballot_sync(FULL, leader && act != 0);  // leaders of the candidates that write
-                unsigned int earlier = wr & ((1u << (grp * GL)) - 1u);
-                while (__any_sync(FULL, earlier != 0)) {
-                    // every lane looks at its own next earlier writer (the lists differ only in length)
-                    const int src = earlier ? __ffs(earlier) - 1 : 0;
-                    const int a_act = __shfl_sync(FULL, act, src);
-                    const float a_fx = __shfl_sync(FULL, fx, src), a_fy = __shfl_sync(FULL, fy, src);
-                    const unsigned int a_best = __shfl_sync(FULL, best, src);
-                    if (earlier && active) {
-                        const float dx = qx - a_fx, dy = qy - a_fy;
-                        const float dist = dx * dx + dy * dy;
-                        if (dist <= size_sq || (a_act == 2 && a_best == best)) conflict = true;
-                    }
-                    earlier &= earlier - 1;
+            if (active) {
+                for (int a = sub; a < grp; a += GL) {
+                    const float4 w = s_step[a];
+                    const int a_act = __float_as_int(w.z);
+                    const float dx = qx - w.x, dy = qy - w.y;
+                    const float dist = dx * dx + dy * dy;
+                    if (a_act != 0 && (dist <= size_sq || (a_act == 2 && __float_as_uint(w.w) == best))) conflict = true;
                 }
             }
-            const unsigned int cmask = __ballot_sync(FULL, conflict && leader);
+            const unsigned int cmask = __ballot_sync(FULL, conflict);
             DSTAT(long long t3 = clock64(); t_conf += t3 - t2;)
             const int n_act = min(KG, n_here - k0);
             const int n_commit = cmask ? min(n_act, (__ffs(cmask) - 1) / GL) : n_act;  // >= 1: group 0 never conflicts
             const bool commits = leader && grp < n_commit;
             const unsigned int amask = __ballot_sync(FULL, commits && act == 1);
             const unsigned int wmask = __ballot_sync(FULL, commits && act != 0);
-            const unsigned int lt = (1u << lane) - 1u;
-            if (commits && act != 0) {
-                const unsigned int key = (act == 1) ? (((unsigned int)L << kKeyShift) | (n_app + __popc(amask & lt))) : best;
-                const unsigned int e = cnt + __popc(wmask & lt);  // < candidates of this level
-                const unsigned int at = beg + e;
-                if (act == 2) P.key[b_at] = kDeadKey;  // the old occupant is dead; it stays on its cell list
-                P.x[at] = fx;
-                P.y[at] = fy;
-                P.resp[at] = resp;
-                P.key[at] = key;
-                const int ncx = min(gw - 1, max(0, (int)fx >> gshift));
-                const int ncy = min(gh - 1, max(0, (int)fy >> gshift));
-                const int ncl = ncy * gw + ncx;
-                // writers that hash to the same cell link in lane order, the others all at once
-                const unsigned int same = __match_any_sync(wmask, ncl);
-                const int rank = __popc(same & lt), nsame = __popc(same);
-                for (int r = 0; r < nsame; r++) {
-                    if (r == rank) {
-                        P.next[at] = h_cur[ncl];
-                        h_cur[ncl] = (unsigned short)e;
-                    }
-                    __syncwarp(same);
+            const unsigned int e = cnt + __popc(wmask & lt);  // the pool index an entry of this candidate gets
+            const int py_before = __shfl_sync(FULL, my_py, (k + 31) & 31);  // row of the candidate before this one
+            if (commits) {
+                if (grp > 0) {
+#pragma unroll 1
+                    for (int r = py_before + 1; r <= py; r++) t_cur[r] = (unsigned short)e;  // a new row starts here
+                }
+                if (act != 0) {
+                    const unsigned int key = (act == 1) ? (((unsigned int)L << kKeyShift) | (n_app + __popc(amask & lt))) : best;
+                    if (act == 2) reinterpret_cast<unsigned int*>(pool + best_at)[3] = kDeadKey;  // the old occupant is dead
+                    pool[beg + e] = make_float4(fx, fy, resp, __uint_as_float(key));
                 }
             }
+            filled = __shfl_sync(FULL, my_py, (k0 + n_commit - 1) & 31);
             n_app += __popc(amask);
             cnt += __popc(wmask);
             k0 += n_commit;
             __syncwarp();
-            __threadfence_block();  // this step's entries and links are visible before the progress moves on
             DSTAT(t_commit += clock64() - t3;)
         }
     }
+#pragma unroll 1
+    for (int r = filled + 1 + lane; r <= lv.h; r += 32) t_cur[r] = (unsigned short)cnt;
 #ifdef AKZ_DEDUP_STATS
     {
-        const unsigned int hops = __reduce_add_sync(FULL, n_hops), cells = __reduce_add_sync(FULL, n_cells);
+        const unsigned int scanned = __reduce_add_sync(FULL, n_scanned);
         if (img == 0 && lane == 0)
-            printf("L%2d cand %6u steps %5u appends %5u entries %5u cells %7u hops %7u | kcycles total %7lld wait %7lld search %7lld conflict %6lld commit %6lld\n", L,
-                   end - beg, n_steps, n_app, cnt, cells, hops, (clock64() - t_all0) / 1000, t_wait / 1000, t_search / 1000, t_conf / 1000, t_commit / 1000);
+            printf("L%2d cand %6u steps %5u appends %5u entries %5u scanned %8u | kcycles total %7lld wait %7lld search %7lld conflict %6lld commit %6lld\n", L,
+                   end - beg, n_steps, n_app, cnt, scanned, (clock64() - t_all0) / 1000, t_wait / 1000, t_search / 1000, t_conf / 1000, t_commit / 1000);
     }
 #endif
+    __syncwarp();
     __threadfence_block();
     if (lane == 0) {
         s_appends[L] = n_app;
@@ -692,47 +694,44 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
     if (s_base[nl] > kp_cap) return;
     // Every live entry goes to its final slot: base of the level that appended it + its index there. The upper-scale filter
     // (scale_space_extrema.rs:111-129) rides along: entry i is dropped if a class i+1 entry in a slot >= i lies within size_i
-    // of it -- the class L+1 entries are exactly the live entries of pool L+1, and their hash grid is still in shared memory,
+    // of it -- the class L+1 entries are exactly the live entries of pool L+1, and its row table is still in shared memory,
     // so the scan over the whole class (quadratic in the keypoint count; 13 x the time for 4.8 x the keypoints at 3840x2160)
-    // becomes a look into at most a handful of cells.
+    // becomes a look at the rows the circle touches.
     keep_flag += (size_t)img * kp_cap;
     const bool has_up = L + 1 < nl;
     const int Lu = has_up ? L + 1 : L;
-    const unsigned short* h_up = s_heads + plan->lgrid_off[Lu];
-    const int ugw = plan->lgrid_w[Lu], ugh = plan->lgrid_h[Lu], ushift = plan->lgrid_shift[Lu];
+    const LevelDev& uv = plan->lv[Lu];
+    const unsigned short* t_up = s_rows + plan->ltab_off[Lu];
     const unsigned int ubeg = lo[Lu];
+    const float u_hr = uv.half_ratio_m1, u_inv = 1.0f / uv.ratio;
     constexpr unsigned int kIdxMask = (1u << kKeyShift) - 1u;
     for (unsigned int e = lane; e < cnt; e += 32) {
-        const unsigned int at = beg + e;
-        const unsigned int key = P.key[at];
+        const float4 rec = pool[beg + e];
+        const unsigned int key = __float_as_uint(rec.w);
         if (key == kDeadKey) continue;
         const unsigned int slot = s_base[key >> kKeyShift] + (key & kIdxMask);
-        const float xi = P.x[at], yi = P.y[at];
+        const float xi = rec.x, yi = rec.y;
         bool repeated = false;
         if (has_up) {
-            const int cx0 = max(0, ((int)floorf(xi - size) - 1) >> ushift), cx1 = min(ugw - 1, ((int)floorf(xi + size) + 1) >> ushift);
-            const int cy0 = max(0, ((int)floorf(yi - size) - 1) >> ushift), cy1 = min(ugh - 1, ((int)floorf(yi + size) + 1) >> ushift);
-            for (int cy = cy0; cy <= cy1 && !repeated; cy++)
-                for (int cx = cx0; cx <= cx1 && !repeated; cx++) {
-                    unsigned short u = h_up[cy * ugw + cx];
-                    while (u != kNil) {
-                        const unsigned int ua = ubeg + u;
-                        const unsigned int ukey = P.key[ua];
-                        if (ukey != kDeadKey && s_base[ukey >> kKeyShift] + (ukey & kIdxMask) >= slot) {  // :115 scans slots j >= i
-                            const float dx = xi - P.x[ua], dy = yi - P.y[ua];
-                            const float dist = dx * dx + dy * dy;
-                            if (dist <= size_sq) {
-                                repeated = true;
-                                break;
-                            }
-                        }
-                        u = P.next[ua];
+            const int u_lo = max(0, (int)floorf((yi - size - u_hr) * u_inv) - 1);
+            const int u_hi = min(uv.h - 1, (int)ceilf((yi + size - u_hr) * u_inv) + 1);
+            const unsigned int j1 = u_lo <= u_hi ? ubeg + t_up[u_hi + 1] : 0u;
+            for (unsigned int j = ubeg + t_up[u_lo]; j < j1; j++) {
+                const float4 up = pool[j];
+                const unsigned int ukey = __float_as_uint(up.w);
+                if (ukey != kDeadKey && s_base[ukey >> kKeyShift] + (ukey & kIdxMask) >= slot) {  // :115 scans slots j >= i
+                    const float dx = xi - up.x, dy = yi - up.y;
+                    const float dist = dx * dx + dy * dy;
+                    if (dist <= size_sq) {
+                        repeated = true;
+                        break;
                     }
                 }
+            }
         }
         c_x[slot] = xi;
         c_y[slot] = yi;
-        c_resp[slot] = P.resp[at];
+        c_resp[slot] = rec.z;
         c_cls[slot] = L;
         keep_flag[slot] = repeated ? 0u : 1u;
     }
@@ -1175,20 +1174,22 @@ k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plan
 
 }  // namespace
 
-template <int KG>
+template <int KG, int MAXT>
 static cudaError_t level_pass_attributes() {
     // see init_detector_attributes: the cache pass must not pin a small shared-memory carveout on the SMs it lives on
-    cudaError_t e = cudaFuncSetAttribute(k_dedup_levels<KG>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_dedup_levels<KG, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess || getenv("AKZ_NO_CARVEOUT") != nullptr) return e;
-    return cudaFuncSetAttribute(k_dedup_levels<KG>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    return cudaFuncSetAttribute(k_dedup_levels<KG, MAXT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
 
 cudaError_t init_keypoint_attributes() {
-    cudaError_t e = level_pass_attributes<8>();
+    cudaError_t e = level_pass_attributes<8, 512>();
     if (e != cudaSuccess) return e;
-    e = level_pass_attributes<16>();
+    e = level_pass_attributes<8, 1024>();
     if (e != cudaSuccess) return e;
-    e = level_pass_attributes<32>();
+    e = level_pass_attributes<16, 512>();
+    if (e != cudaSuccess) return e;
+    e = level_pass_attributes<16, 1024>();
     if (e != cudaSuccess) return e;
     if (getenv("AKZ_NO_CARVEOUT") != nullptr) return cudaSuccess;
     e = cudaFuncSetAttribute(k_dedup_smem, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1198,27 +1199,34 @@ cudaError_t init_keypoint_attributes() {
 
 size_t dedup_pool_bytes(const Plan& P) { return (size_t)P.dev.pool_cap * kPoolBytesPerEntry; }
 size_t dedup_level_pool_bytes(uint32_t cand_cap) { return (size_t)cand_cap * kLevelPoolBytesPerCand; }
-static size_t level_pass_smem(const Plan& P) { return (size_t)P.dev.lgrid_off[P.dev.n_levels] * sizeof(unsigned short); }
+template <int KG>
+static size_t level_pass_smem(const Plan& P) {
+    return (size_t)P.dev.n_levels * KG * sizeof(uint4) + (size_t)P.dev.ltab_off[P.dev.n_levels] * sizeof(unsigned short);
+}
 
 template <int KG>
-static void launch_level_pass(const Launch& L, const Plan& P, const Buffers& B, size_t smem) {
-    k_dedup_levels<KG><<<L.batch, 32 * P.dev.n_levels, smem, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap,
-                                                                         L.kp_cap, B.c_x, B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags,
-                                                                         B.level_pool, B.keep_flag, B.upper_done);
+static void launch_level_pass(const Launch& L, const Plan& P, const Buffers& B) {
+    // 512-thread blocks (the default 16 levels) may use 128 registers per thread, 1024-thread ones 64
+    const size_t smem = level_pass_smem<KG>(P);
+    if (P.dev.n_levels <= 16)
+        k_dedup_levels<KG, 512><<<L.batch, 32 * P.dev.n_levels, smem, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch,
+                                                                                  L.cand_cap, L.kp_cap, B.c_x, B.c_y, B.c_resp, B.c_cls, B.n_cache,
+                                                                                  B.err_flags, B.level_pool, B.keep_flag, B.upper_done);
+    else
+        k_dedup_levels<KG, 1024><<<L.batch, 32 * P.dev.n_levels, smem, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch,
+                                                                                   L.cand_cap, L.kp_cap, B.c_x, B.c_y, B.c_resp, B.c_cls, B.n_cache,
+                                                                                   B.err_flags, B.level_pool, B.keep_flag, B.upper_done);
 }
 
 int launch_dedup(const Launch& L, const Plan& P, const Buffers& B) {
     // every image is handled by exactly one of the two kernels launched here (image_fits_*_pass)
     static const bool single_warp = getenv("AKZ_DEDUP_SINGLE") != nullptr;  // A/B switch: the one-warp-per-image pass
-    const size_t smem = level_pass_smem(P);
-    const bool levels = !single_warp && smem <= 200 * 1024;
     static const int groups = getenv("AKZ_DEDUP_GROUPS") ? atoi(getenv("AKZ_DEDUP_GROUPS")) : 8;  // A/B switch: candidates per step
-    if (levels && groups == 32) {
-        launch_level_pass<32>(L, P, B, smem);
-    } else if (levels && groups == 16) {
-        launch_level_pass<16>(L, P, B, smem);
+    const bool levels = !single_warp && level_pass_smem<16>(P) <= 200 * 1024;
+    if (levels && groups == 16) {
+        launch_level_pass<16>(L, P, B);
     } else if (levels) {
-        launch_level_pass<8>(L, P, B, smem);
+        launch_level_pass<8>(L, P, B);
     } else {
         k_dedup_smem<<<L.batch, 32, 0, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap, L.kp_cap, B.c_x,
                                                    B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags, B.dedup_pool, B.upper_done);
