@@ -357,6 +357,25 @@ struct akz_context {
     Results res;
     int cur_batch = 0;
     uint32_t n_sub_batches = 0;
+    // a call that is one sub-batch long (a single image, a small batch) is launch-bound: ~90 launches and ~70 event
+    // operations cost the host more than the kernels cost the GPU. Its launch sequence is captured once into a CUDA graph
+    // and replayed while nothing it depends on changes (GraphKey).
+    struct GraphKey {
+        uint64_t alloc_epoch = 0;
+        const void* in = nullptr;
+        const void* stats = nullptr;
+        size_t stride = 0;
+        uint32_t n = 0, cand_cap = 0, kp_cap = 0;
+        bool is_u8 = false;
+        bool operator==(const GraphKey& o) const {
+            return alloc_epoch == o.alloc_epoch && in == o.in && stats == o.stats && stride == o.stride && n == o.n && cand_cap == o.cand_cap &&
+                   kp_cap == o.kp_cap && is_u8 == o.is_u8;
+        }
+    };
+    cudaGraphExec_t graph_exec = nullptr;
+    GraphKey graph_key;
+    int graph_launches = 0;
+    uint64_t graph_replays = 0;
     std::vector<std::pair<uint32_t, uint32_t>> sched;  // (first image, count) of every sub-batch of the current call
     // per-stage timing
     bool timing = false;
@@ -429,9 +448,12 @@ static void free_buffers(akz_context* c) {
     free_results(c->res);
 }
 
+static std::atomic<uint64_t> g_alloc_epoch{1};  // bumped by every device allocation: a captured graph holds raw pointers
+
 template <class T>
 static cudaError_t dalloc(std::vector<void*>& owner, T** p, size_t count) {
     void* v = nullptr;
+    g_alloc_epoch++;
     cudaError_t e = cudaMalloc(&v, std::max<size_t>(count, 1) * sizeof(T));
     if (e != cudaSuccess) return e;
     owner.push_back(v);
@@ -680,13 +702,11 @@ static void harvest_timing(akz_context* c) {
 // On return everything has been ISSUED and c->stream waits for all of it.
 // `upload`, when given, enqueues the host -> device copy of one sub-batch on the copy stream and records ev_copy[sb]; it is
 // called one sub-batch ahead of the kernels that consume it.
-static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8, size_t in_stride,
-                        const std::function<int(uint32_t)>& upload = nullptr) {
+static int issue_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8, size_t in_stride,
+                          const std::function<int(uint32_t)>& upload, bool capturing, int* launches) {
     const bool wait_copies = (bool)upload;
     const Plan& P = c->plan;
     const Results& R = c->res;
-    c->generation++;
-    c->cur_batch = (int)n;
     const size_t in_img = in_stride * P.h * (is_u8 ? 1 : sizeof(float));  // bytes per input image
     int k = 0, j;
 #define STAGE(st, strm, expr)          \
@@ -830,15 +850,73 @@ static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8
         int rc = finish_sub_batch(prev);
         if (rc != AKZ_OK) return rc;
     }
-    c->n_sub_batches = (uint32_t)c->sched.size();
 #undef STAGE
     for (int l = 0; l < 2; l++)
         if (c->lane[l].busy) {
             CK(cudaStreamWaitEvent(c->stream, c->lane[l].ev_done, 0));
             c->lane[l].busy = false;
         }
-    c->launches += (uint64_t)k;
+    // a capture ends on c->stream with every forked stream joined: the statistics copies are the last thing on the side stream
+    if (capturing) CK(cudaStreamWaitEvent(c->stream, c->ev_stats[c->sched.size() - 1], 0));
+    *launches = k;
     CK(cudaGetLastError());
+    return AKZ_OK;
+}
+
+static void drop_graph(akz_context* c) {
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    c->graph_exec = nullptr;
+}
+
+static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8, size_t in_stride,
+                        const std::function<int(uint32_t)>& upload = nullptr) {
+    static const bool no_graph = getenv("AKZ_NO_GRAPH") != nullptr;  // A/B switch: always issue the launches one by one
+    c->generation++;
+    c->cur_batch = (int)n;
+    c->n_sub_batches = (uint32_t)c->sched.size();
+    int k = 0;
+    const bool graph_ok = !no_graph && !c->timing && c->sched.size() == 1 && !(c->flags & AKZ_KEEP_EVOLUTIONS);
+    if (!graph_ok) {
+        int rc = issue_pipeline(c, n, d_in, is_u8, in_stride, upload, false, &k);
+        c->launches += (uint64_t)k;
+        return rc;
+    }
+    if (upload) {  // the inputs travel outside the graph, on the copy stream as always
+        int rc = upload(0);
+        if (rc != AKZ_OK) return rc;
+        CK(cudaStreamWaitEvent(c->stream, c->ev_copy[0], 0));
+    }
+    akz_context::GraphKey key;
+    key.alloc_epoch = g_alloc_epoch.load();
+    key.in = d_in;
+    key.stats = c->hs.n_kp;
+    key.stride = in_stride;
+    key.n = n;
+    key.cand_cap = c->cand_cap;
+    key.kp_cap = c->kp_cap;
+    key.is_u8 = is_u8;
+    if (!c->graph_exec || !(key == c->graph_key)) {
+        drop_graph(c);
+        CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
+        int rc = issue_pipeline(c, n, d_in, is_u8, in_stride, nullptr, true, &k);
+        cudaGraph_t g = nullptr;
+        cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+        if (rc != AKZ_OK) {
+            if (g) cudaGraphDestroy(g);
+            return rc;
+        }
+        CK(e);
+        e = cudaGraphInstantiate(&c->graph_exec, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) c->graph_exec = nullptr;
+        CK(e);
+        c->graph_key = key;
+        c->graph_launches = k;
+    }
+    CK(cudaGraphLaunch(c->graph_exec, c->stream));
+    CK(cudaEventRecord(c->ev_stats[0], c->stream));  // what the host waits for before it reads the statistics
+    c->graph_replays++;
+    c->launches += (uint64_t)c->graph_launches;
     return AKZ_OK;
 }
 
@@ -1046,6 +1124,7 @@ void akz_destroy(akz_context* c) {
             if (c->lane[l].ev_det[i]) cudaEventDestroy(c->lane[l].ev_det[i]);
         }
     }
+    drop_graph(c);
     cudaStreamDestroy(c->stream_kp);
     cudaStreamSynchronize(c->stream_det);
     cudaStreamDestroy(c->stream_det);

@@ -488,6 +488,9 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
     const float ratio = lv.ratio, size = lv.kp_size, size_sq = lv.size_sq, hr = lv.half_ratio_m1;
     const float inv_ratio = 1.0f / ratio, p_ratio = pv.ratio, p_hr = pv.half_ratio_m1, p_inv = 1.0f / pv.ratio;
     const int p_rows = pv.h;
+    // an entry whose row lies more than size above or below a point cannot be within size of it; rows (y * ratio + hr) and
+    // points are exact in f32, the 0.01 px cover the rounding of the squared distance and of size * size
+    const float reach = size + 0.01f;
     const int margin = L > 0 ? (int)ceilf(size + pv.kp_size) + 4 * (int)p_ratio + 6 : 0;
     const float* ldet = ldet_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
     const unsigned int lw = (unsigned int)lv.w;
@@ -558,13 +561,13 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
             if (active) {
                 // this level's entries from the first row the circle can touch (not past the rows closed above) to the newest,
                 // then the rows of level L-1 it can touch; one index space, eight independent loads in flight per lane
-                const int r_lo = max(0, min(r0, (int)floorf((qy - size - hr) * inv_ratio) - 1));
+                const int r_lo = max(0, min(r0, (int)ceilf((qy - reach - hr) * inv_ratio)));
                 const unsigned int i0 = beg + t_cur[r_lo];
                 const unsigned int n_cur = beg + cnt - i0;
                 unsigned int j0 = 0, n_tot = n_cur;
                 if (L > 0) {
-                    const int p_lo = max(0, (int)floorf((qy - size - p_hr) * p_inv) - 1);
-                    const int p_hi = min(p_rows - 1, (int)ceilf((qy + size - p_hr) * p_inv) + 1);
+                    const int p_lo = max(0, (int)ceilf((qy - reach - p_hr) * p_inv));
+                    const int p_hi = min(p_rows - 1, (int)floorf((qy + reach - p_hr) * p_inv));
                     if (p_lo <= p_hi) {
                         j0 = pbeg + t_prv[p_lo];
                         n_tot += pbeg + t_prv[p_hi + 1] - j0;
@@ -713,8 +716,8 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
         const float xi = rec.x, yi = rec.y;
         bool repeated = false;
         if (has_up) {
-            const int u_lo = max(0, (int)floorf((yi - size - u_hr) * u_inv) - 1);
-            const int u_hi = min(uv.h - 1, (int)ceilf((yi + size - u_hr) * u_inv) + 1);
+            const int u_lo = max(0, (int)ceilf((yi - reach - u_hr) * u_inv));
+            const int u_hi = min(uv.h - 1, (int)floorf((yi + reach - u_hr) * u_inv));
             const unsigned int j1 = u_lo <= u_hi ? ubeg + t_up[u_hi + 1] : 0u;
             for (unsigned int j = ubeg + t_up[u_lo]; j < j1; j++) {
                 const float4 up = pool[j];
