@@ -290,6 +290,7 @@ struct Lane {
     int alloc_batch = 0;
     cudaEvent_t ev_stencil = nullptr;  // stage A of the sub-batch using this lane has finished
     cudaEvent_t ev_dedup = nullptr;    // the cache pass of the sub-batch using this lane has finished
+    cudaEvent_t ev_compact = nullptr;  // the candidate lists of the first part of a two-part cache pass are written
     cudaEvent_t ev_done = nullptr;     // stage B of the sub-batch using this lane has finished
     cudaEvent_t ev_prep[kMaxLevels] = {nullptr};  // Lsmooth_l (and for level 1 the consumers of the stored gradients) ready
     cudaEvent_t ev_det[kMaxLevels] = {nullptr};   // detector(l) has finished
@@ -508,7 +509,7 @@ static int ensure_lane(akz_context* c, Lane& ln, int batch) {
     CK(dalloc(A, &B.c_next, kc));
     CK(dalloc(A, &B.grid, nb * 2 * (size_t)P.dev.grid_w * P.dev.grid_h));
     CK(dalloc(A, &B.dedup_pool, nb * dedup_pool_bytes(P)));
-    CK(dalloc(A, &B.level_pool, nb * dedup_level_pool_bytes(c->cand_cap)));
+    CK(dalloc(A, &B.level_pool, nb * dedup_level_pool_bytes(P, c->cand_cap)));
     CK(dalloc(A, &B.keep_flag, kc));
     CK(dalloc(A, &B.cls_range, nb * kMaxLevels * 2));
     CK(dalloc(A, &B.upper_done, nb));
@@ -518,6 +519,7 @@ static int ensure_lane(akz_context* c, Lane& ln, int batch) {
         CK(cudaEventCreateWithFlags(&ln.ev_stencil, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ln.ev_done, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ln.ev_dedup, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ln.ev_compact, cudaEventDisableTiming));
         for (int l = 0; l < kMaxLevels; l++) {
             CK(cudaEventCreateWithFlags(&ln.ev_prep[l], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ln.ev_det[l], cudaEventDisableTiming));
@@ -643,7 +645,7 @@ static int prepare(akz_context* c, uint32_t n, uint32_t w, uint32_t h, const akz
             CK(cudaMemGetInfo(&free_b, &total_b));
             const size_t n0 = (size_t)w * h;
             const size_t per_image = 4 * (4 * (size_t)np.dev.plane_px + 4 * n0) + 4 * (size_t)np.dev.mask_words + 4 * (size_t)c->cand_cap +
-                                     40 * (size_t)c->kp_cap + dedup_pool_bytes(np) + dedup_level_pool_bytes(c->cand_cap) + (1 << 16);
+                                     40 * (size_t)c->kp_cap + dedup_pool_bytes(np) + dedup_level_pool_bytes(np, c->cand_cap) + (1 << 16);
             const size_t fit = (free_b / 2) / (2 * per_image);
             c->sub_batch = (uint32_t)std::max<size_t>(16, std::min<size_t>(256, fit));
         }
@@ -797,6 +799,24 @@ static int issue_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_
         STAGE(AKZ_STAGE_CONTRAST, c->stream, launch_contrast(LA, P, B));
         STAGE(AKZ_STAGE_DETECTOR, sd, launch_detector(LD, P, B, 0));
         if (split) CK(cudaEventRecord(ln.ev_det[0], sd));
+        // A sub-batch with nothing behind it (a single image, the last of a call) cannot hide its cache pass behind the next
+        // one's stencil kernels. It runs the pass in two parts instead: the first octave's levels (most of the candidates) as
+        // soon as their detectors are through, on the side stream, next to the stencil kernels of the other octaves.
+        const bool last = (sb + 1 == (uint32_t)c->sched.size());
+        const int pass_cut = (split && last) ? dedup_split_level(P) : 0;
+        auto first_part = [&](int l) -> int {
+            if (l != pass_cut - 1) return AKZ_OK;
+            CK(cudaStreamWaitEvent(c->stream_kp, ln.ev_det[l], 0));
+            Launch LK{c->stream_kp, (int)cnt, c->cand_cap, c->kp_cap};
+            k += launch_compact(LK, P, B, 0, pass_cut);
+            CK(cudaEventRecord(ln.ev_compact, c->stream_kp));
+            k += launch_dedup(LK, P, B, 0, pass_cut);
+            return AKZ_OK;
+        };
+        if (pass_cut) {
+            int rc = first_part(0);
+            if (rc != AKZ_OK) return rc;
+        }
         for (int l = 1; l < P.dev.n_levels; l++) {
             if (split && l >= 2) CK(cudaStreamWaitEvent(c->stream, ln.ev_det[l - 2], 0));  // its Lsmooth scratch plane is free again
             STAGE(AKZ_STAGE_PREP, c->stream, launch_prep(LA, P, B, l));
@@ -808,21 +828,25 @@ static int issue_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_
             }
             STAGE(AKZ_STAGE_DETECTOR, sd, launch_detector(LD, P, B, l));
             if (split) CK(cudaEventRecord(ln.ev_det[l], sd));
+            if (pass_cut) {
+                int rc = first_part(l);
+                if (rc != AKZ_OK) return rc;
+            }
         }
         if (split) CK(cudaStreamWaitEvent(c->stream, ln.ev_det[P.dev.n_levels - 1], 0));
-        STAGE(AKZ_STAGE_COMPACT, c->stream, launch_compact(LA, P, B));
+        if (pass_cut) CK(cudaStreamWaitEvent(c->stream, ln.ev_compact, 0));  // the lists of the other levels go behind the first part's
+        STAGE(AKZ_STAGE_COMPACT, c->stream, launch_compact(LA, P, B, pass_cut, P.dev.n_levels));
         CK(cudaEventRecord(ln.ev_stencil, c->stream));
         // Order on the main stream: S(0) S(1) F(0) S(2) F(1) ... ; the cache pass D(i) starts on the side stream once
         // both S(i) and F(i-1) are through, so that it runs next to the stencil kernels of S(i+1) (one-warp and
         // four-warp blocks that still fit beside it) and not next to the descriptor kernel, whose four 256-thread blocks
         // need the whole register file of an SM: with a cache-pass warp resident only three fit (measured: descriptors
         // +22 %, filter/orientation +20 %). The last sub-batch has nothing behind it, so its cache pass goes first.
-        const bool last = (sb + 1 == (uint32_t)c->sched.size());
         auto launch_cache_pass = [&]() -> int {
             CK(cudaStreamWaitEvent(c->stream_kp, ln.ev_stencil, 0));
             if (have_prev && !last) CK(cudaStreamWaitEvent(c->stream_kp, prev.ln->ev_done, 0));
             Launch LB{c->stream_kp, (int)cnt, c->cand_cap, c->kp_cap};
-            STAGE(AKZ_STAGE_DEDUP, c->stream_kp, launch_dedup(LB, P, B));
+            STAGE(AKZ_STAGE_DEDUP, c->stream_kp, launch_dedup(LB, P, B, pass_cut, P.dev.n_levels));
             CK(cudaEventRecord(ln.ev_dedup, c->stream_kp));
             // timing mode (and the A/B switch) runs the cache pass alone, so that every stage's event pair brackets its kernels only
             static const bool serial_lanes = getenv("AKZ_SERIAL_LANES") != nullptr;
@@ -1119,6 +1143,7 @@ void akz_destroy(akz_context* c) {
         if (c->lane[l].ev_stencil) cudaEventDestroy(c->lane[l].ev_stencil);
         if (c->lane[l].ev_done) cudaEventDestroy(c->lane[l].ev_done);
         if (c->lane[l].ev_dedup) cudaEventDestroy(c->lane[l].ev_dedup);
+        if (c->lane[l].ev_compact) cudaEventDestroy(c->lane[l].ev_compact);
         for (int i = 0; i < kMaxLevels; i++) {
             if (c->lane[l].ev_prep[i]) cudaEventDestroy(c->lane[l].ev_prep[i]);
             if (c->lane[l].ev_det[i]) cudaEventDestroy(c->lane[l].ev_det[i]);

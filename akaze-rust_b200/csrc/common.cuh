@@ -165,12 +165,15 @@ int launch_fed(const Launch& L, const Plan& P, const Buffers& B, int level);
 cudaError_t init_detector_attributes();
 cudaError_t init_scale_space_attributes();
 int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level);
-int launch_compact(const Launch& L, const Plan& P, const Buffers& B);
+int launch_compact(const Launch& L, const Plan& P, const Buffers& B, int l0 = 0, int l1 = -1);  // levels [l0, l1), -1 = all
 // keypoints.cu
 cudaError_t init_keypoint_attributes();
 size_t dedup_pool_bytes(const Plan& P);
-size_t dedup_level_pool_bytes(uint32_t cand_cap);
-int launch_dedup(const Launch& L, const Plan& P, const Buffers& B);
+size_t dedup_level_pool_bytes(const Plan& P, uint32_t cand_cap);
+// levels [l0, l1) of the cache pass; the call that ends at the last level also assigns the final slots. split_level(): where a
+// two-part pass is cut (0 = this plan does not split)
+int launch_dedup(const Launch& L, const Plan& P, const Buffers& B, int l0 = 0, int l1 = -1);
+int dedup_split_level(const Plan& P);
 int launch_finalize(const Launch& L, const Plan& P, const Buffers& B);
 int launch_descriptors(const Launch& L, const Plan& P, const Buffers& B);
 // matcher.cu

@@ -919,12 +919,13 @@ __device__ __forceinline__ int find_level(const PlanDev* plan, int grow, int* ro
     return l;
 }
 
+// (the three kernels work on the global rows [row0, row1): the levels [l0, l1) of one launch_compact call)
 __global__ void k_rowcount(const unsigned int* __restrict__ mask, const PlanDev* __restrict__ plan,
-                           unsigned int* __restrict__ rowcount, int total_rows) {
+                           unsigned int* __restrict__ rowcount, int total_rows, int row0, int row1) {
     const int lane = threadIdx.x & 31;
-    const int grow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int grow = row0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int img = blockIdx.y;
-    if (grow >= total_rows) return;
+    if (grow >= row1) return;
     int y;
     const int l = find_level(plan, grow, &y);
     const LevelDev& lv = plan->lv[l];
@@ -940,17 +941,18 @@ __global__ void k_rowcount(const unsigned int* __restrict__ mask, const PlanDev*
 // one block per image: exclusive scan of the row counts, per-level offsets, total
 __global__ void __launch_bounds__(1024)
 k_rowscan(unsigned int* __restrict__ rowcount, const PlanDev* __restrict__ plan, unsigned int* __restrict__ level_off,
-          unsigned int* __restrict__ n_total, unsigned int* __restrict__ err_flags, int total_rows, unsigned int cand_cap) {
+          unsigned int* __restrict__ n_total, unsigned int* __restrict__ err_flags, int total_rows, unsigned int cand_cap, int row0,
+          int row1, int l0, int l1) {
     __shared__ unsigned int warp_sums[32];
     __shared__ unsigned int carry;
     const int img = blockIdx.x;
     unsigned int* rc = rowcount + (size_t)img * total_rows;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (tid == 0) carry = 0;
+    if (tid == 0) carry = l0 > 0 ? level_off[(size_t)img * (kMaxLevels + 1) + l0] : 0u;  // where the levels before l0 ended
     __syncthreads();
-    for (int base = 0; base < total_rows; base += 1024) {
+    for (int base = row0; base < row1; base += 1024) {
         const int i = base + tid;
-        const unsigned int v = (i < total_rows) ? rc[i] : 0;
+        const unsigned int v = (i < row1) ? rc[i] : 0;
         unsigned int incl = v;
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
@@ -969,31 +971,34 @@ k_rowscan(unsigned int* __restrict__ rowcount, const PlanDev* __restrict__ plan,
         __syncthreads();
         const unsigned int woff = wid ? warp_sums[wid - 1] : 0;
         const unsigned int excl = carry + woff + incl - v;
-        if (i < total_rows) rc[i] = excl;
+        if (i < row1) rc[i] = excl;
         __syncthreads();
         if (tid == 1023) carry = excl + v;
         __syncthreads();
     }
     if (tid == 0) {
-        // per-level offsets from the scanned rows
-        int row = 0;
-        for (int l = 0; l < plan->n_levels; l++) {
-            level_off[(size_t)img * (kMaxLevels + 1) + l] = (row < total_rows) ? rc[row] : carry;
+        // per-level offsets from the scanned rows; the entry after the last level of this call is the running total
+        int row = row0;
+        for (int l = l0; l < l1; l++) {
+            level_off[(size_t)img * (kMaxLevels + 1) + l] = (row < row1) ? rc[row] : carry;
             row += plan->lv[l].h;
         }
-        for (int l = plan->n_levels; l <= kMaxLevels; l++) level_off[(size_t)img * (kMaxLevels + 1) + l] = carry;
-        n_total[img] = carry;
+        level_off[(size_t)img * (kMaxLevels + 1) + l1] = carry;
+        if (l1 == plan->n_levels) {
+            for (int l = l1; l <= kMaxLevels; l++) level_off[(size_t)img * (kMaxLevels + 1) + l] = carry;
+            n_total[img] = carry;
+        }
         if (carry > cand_cap) atomicOr(&err_flags[img], (unsigned int)kErrCandOverflow);
     }
 }
 
 __global__ void k_scatter(const unsigned int* __restrict__ mask, const PlanDev* __restrict__ plan,
                           const unsigned int* __restrict__ rowoff, unsigned int* __restrict__ cand, int total_rows,
-                          unsigned int cand_cap) {
+                          unsigned int cand_cap, int row0, int row1) {
     const int lane = threadIdx.x & 31;
-    const int grow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int grow = row0 + blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int img = blockIdx.y;
-    if (grow >= total_rows) return;
+    if (grow >= row1) return;
     int y;
     const int l = find_level(plan, grow, &y);
     const LevelDev& lv = plan->lv[l];
@@ -1165,16 +1170,22 @@ int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level)
     return 1;
 }
 
-int launch_compact(const Launch& L, const Plan& P, const Buffers& B) {
-    int total_rows = 0;
-    for (int l = 0; l < P.dev.n_levels; l++) total_rows += P.dev.lv[l].h;
+int launch_compact(const Launch& L, const Plan& P, const Buffers& B, int l0, int l1) {
+    // candidate lists of the levels [l0, l1), appended behind those of the levels before l0 (compacted by an earlier call)
+    if (l1 < 0) l1 = P.dev.n_levels;
+    int total_rows = 0, row0 = 0, row1 = 0;
+    for (int l = 0; l < P.dev.n_levels; l++) {
+        if (l < l0) row0 += P.dev.lv[l].h;
+        if (l < l1) row1 += P.dev.lv[l].h;
+        total_rows += P.dev.lv[l].h;
+    }
     unsigned int* rowcount = B.rowcount;  // [B][total_rows]
     const int wpb = 8;
-    dim3 grid((total_rows + wpb - 1) / wpb, L.batch);
-    k_rowcount<<<grid, wpb * 32, 0, L.stream>>>(B.mask, B.plan_dev, rowcount, total_rows);
+    dim3 grid((row1 - row0 + wpb - 1) / wpb, L.batch);
+    k_rowcount<<<grid, wpb * 32, 0, L.stream>>>(B.mask, B.plan_dev, rowcount, total_rows, row0, row1);
     k_rowscan<<<L.batch, 1024, 0, L.stream>>>(rowcount, B.plan_dev, B.cand_level_count, B.n_cand_total, B.err_flags,
-                                              total_rows, L.cand_cap);
-    k_scatter<<<grid, wpb * 32, 0, L.stream>>>(B.mask, B.plan_dev, rowcount, B.cand, total_rows, L.cand_cap);
+                                              total_rows, L.cand_cap, row0, row1, l0, l1);
+    k_scatter<<<grid, wpb * 32, 0, L.stream>>>(B.mask, B.plan_dev, rowcount, B.cand, total_rows, L.cand_cap, row0, row1);
     return 3;
 }
 

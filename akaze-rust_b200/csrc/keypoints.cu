@@ -20,7 +20,7 @@ namespace akz {
 namespace {
 
 __device__ __forceinline__ bool image_fits_smem_pass(const PlanDev* plan, const unsigned int* lo);
-__device__ __forceinline__ bool image_fits_level_pass(const PlanDev* plan, const unsigned int* lo);
+__device__ __forceinline__ bool image_fits_level_pass(const PlanDev* plan, const unsigned int* lo, int n);
 
 // ------------------------------------------------------------------------------------------------
 // K5a: greedy cache pass, one warp per image, working set in global memory (fallback for images whose
@@ -50,7 +50,7 @@ k_dedup(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ cand,
         return;
     }
     // handled by the fast pass that runs beside this kernel (1 = k_dedup_levels, 0 = k_dedup_smem)
-    if (fast_pass == 1 ? image_fits_level_pass(plan, lo) : image_fits_smem_pass(plan, lo)) return;
+    if (fast_pass == 1 ? image_fits_level_pass(plan, lo, plan->n_levels) : image_fits_smem_pass(plan, lo)) return;
     if (lane == 0) upper_done[img] = 0;  // k_filter_refine runs the upper-scale scan for this image
     unsigned int n = 0;  // cache length (uniform across lanes)
     bool overflow = false;
@@ -430,8 +430,9 @@ constexpr unsigned int kDeadKey = 0xffffffffu;
 constexpr int kKeyShift = 20;               // key = (level of the append << 20) | index of the append inside its level
 constexpr unsigned int kMaxLevelCands = 65534;  // row tables hold u16 indices
 
-__device__ __forceinline__ bool image_fits_level_pass(const PlanDev* plan, const unsigned int* lo) {
-    for (int l = 0; l < plan->n_levels; l++)
+// (the levels [0, n): a first part of the pass only knows the offsets of its own levels)
+__device__ __forceinline__ bool image_fits_level_pass(const PlanDev* plan, const unsigned int* lo, int n) {
+    for (int l = 0; l < n; l++)
         if (lo[l + 1] - lo[l] > kMaxLevelCands) return false;
     return true;
 }
@@ -446,33 +447,42 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
                const float* __restrict__ ldet_plane, int batch, unsigned int cand_cap, unsigned int kp_cap, float* __restrict__ c_x,
                float* __restrict__ c_y, float* __restrict__ c_resp, int* __restrict__ c_cls, unsigned int* __restrict__ n_cache,
                unsigned int* __restrict__ err_flags, unsigned char* pools, unsigned int* __restrict__ keep_flag,
-               unsigned int* __restrict__ upper_done) {
+               unsigned int* __restrict__ upper_done, size_t slab_bytes, int l0, int l1) {
+    // This launch walks the levels [l0, l1). One launch for all of them is the plain pass. A sub-batch with nothing to hide
+    // behind (a single image, the last of a call) runs it in two: the first octave as soon as its detectors are through, next
+    // to the stencil kernels of the other octaves, the rest at the end. The first part leaves its row tables and counts in
+    // the image's slab, the part that ends at the last level reloads them and assigns the final slots for every level.
     extern __shared__ uint4 s_dyn[];  // per level KG step records (float4), then the row tables (u16, level l at ltab_off[l])
     __shared__ volatile int s_progress[kMaxLevels];
     __shared__ unsigned int s_appends[kMaxLevels], s_base[kMaxLevels + 1];
     __shared__ int s_ok;
     const unsigned int FULL = 0xffffffffu;
     const int img = blockIdx.x;
-    const int lane = threadIdx.x & 31, L = threadIdx.x >> 5;  // one warp per level
     const int nl = plan->n_levels;
-    float4* s_step = reinterpret_cast<float4*>(s_dyn) + L * KG;
+    const bool final_part = l1 == nl;  // (then the block has a warp for every level, else one for each of [l0, l1))
+    const int lane = threadIdx.x & 31, L = (threadIdx.x >> 5) + (final_part ? 0 : l0);  // one warp per level
+    float4* s_step = reinterpret_cast<float4*>(s_dyn) + (threadIdx.x >> 5) * KG;
     unsigned short* s_rows = reinterpret_cast<unsigned short*>(s_dyn + nl * KG);
     const unsigned int* cl = cand + (size_t)img * cand_cap;
     const unsigned int* lo = level_off + (size_t)img * (kMaxLevels + 1);
-    if (threadIdx.x == 0) s_ok = !(err_flags[img] & kErrCandOverflow) && image_fits_level_pass(plan, lo);
+    unsigned char* slab = pools + (size_t)img * slab_bytes;  // pool entries, then the row tables, then (appends, entries) per level
+    float4* pool = reinterpret_cast<float4*>(slab);
+    unsigned short* g_rows = reinterpret_cast<unsigned short*>(slab + (size_t)cand_cap * kLevelPoolBytesPerCand);
+    unsigned int* g_meta = reinterpret_cast<unsigned int*>(g_rows + plan->ltab_off[nl]);
+    if (threadIdx.x == 0) s_ok = !(err_flags[img] & kErrCandOverflow) && image_fits_level_pass(plan, lo, l1);
     if (threadIdx.x < kMaxLevels) {
-        s_progress[threadIdx.x] = -1;
-        s_appends[threadIdx.x] = 0;
+        s_progress[threadIdx.x] = threadIdx.x < l0 ? 0x7fffffff : -1;  // the levels of an earlier part are finished
+        s_appends[threadIdx.x] = threadIdx.x < l0 ? g_meta[2 * threadIdx.x] : 0u;
     }
+    for (int i = threadIdx.x; i < plan->ltab_off[l0]; i += blockDim.x) s_rows[i] = g_rows[i];
     __syncthreads();
     if (!s_ok) {  // candidate overflow: nothing to do; a level beyond the u16 tables: k_dedup takes the image
-        if (threadIdx.x == 0 && (err_flags[img] & kErrCandOverflow)) {
+        if (threadIdx.x == 0 && final_part && (err_flags[img] & kErrCandOverflow)) {
             n_cache[img] = 0;
             upper_done[img] = 0;
         }
         return;
     }
-    float4* pool = reinterpret_cast<float4*>(pools + (size_t)img * ((size_t)cand_cap * kLevelPoolBytesPerCand));
     c_x += (size_t)img * kp_cap;
     c_y += (size_t)img * kp_cap;
     c_resp += (size_t)img * kp_cap;
@@ -494,16 +504,17 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
     const int margin = L > 0 ? (int)ceilf(size + pv.kp_size) + 4 * (int)p_ratio + 6 : 0;
     const float* ldet = ldet_plane + (size_t)lv.off * batch + (size_t)img * lv.w * lv.h;
     const unsigned int lw = (unsigned int)lv.w;
-    unsigned int n_app = 0;  // appends of this level (uniform across the warp)
-    unsigned int cnt = 0;    // pool entries of this level (appends + replacements)
+    const bool walks = L >= l0;  // (a final part: the warps of the levels before l0 only take part in the slot assignment)
+    unsigned int n_app = walks ? 0u : g_meta[2 * L];      // appends of this level (uniform across the warp)
+    unsigned int cnt = walks ? 0u : g_meta[2 * L + 1];    // pool entries of this level (appends + replacements)
     int filled = 0;          // t_cur[0 .. filled] are final
     int seen = -1;           // the last progress of level L-1 this warp has read
-    if (lane == 0) t_cur[0] = 0;
+    if (lane == 0 && walks) t_cur[0] = 0;
 
     // the 32 candidates of a batch, one per lane: position in the level, response
     int nx_px = 0, nx_py = 0;
     float nx_resp = 0.0f;
-    if (beg + lane < end) {
+    if (walks && beg + lane < end) {
         const unsigned int f = cl[beg + lane];
         nx_py = (int)(f / lw);
         nx_px = (int)(f - (unsigned int)nx_py * lw);
@@ -520,7 +531,7 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
 #else
 #define DSTAT(x)
 #endif
-    for (unsigned int base = beg; base < end; base += 32) {
+    for (unsigned int base = walks ? beg : end; base < end; base += 32) {
         const int my_px = nx_px, my_py = nx_py;
         const float my_resp = nx_resp;
         if (base + 32 + lane < end) {
@@ -661,8 +672,10 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
             DSTAT(t_commit += clock64() - t3;)
         }
     }
+    if (walks) {
 #pragma unroll 1
-    for (int r = filled + 1 + lane; r <= lv.h; r += 32) t_cur[r] = (unsigned short)cnt;
+        for (int r = filled + 1 + lane; r <= lv.h; r += 32) t_cur[r] = (unsigned short)cnt;
+    }
 #ifdef AKZ_DEDUP_STATS
     {
         const unsigned int scanned = __reduce_add_sync(FULL, n_scanned);
@@ -676,6 +689,14 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
     if (lane == 0) {
         s_appends[L] = n_app;
         s_progress[L] = 0x7fffffff;  // level finished
+    }
+    if (!final_part) {  // leave the table and the counts for the part that follows
+        for (int r = lane; r <= lv.h; r += 32) g_rows[plan->ltab_off[L] + r] = t_cur[r];
+        if (lane == 0) {
+            g_meta[2 * L] = n_app;
+            g_meta[2 * L + 1] = cnt;
+        }
+        return;
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1201,39 +1222,64 @@ cudaError_t init_keypoint_attributes() {
 }
 
 size_t dedup_pool_bytes(const Plan& P) { return (size_t)P.dev.pool_cap * kPoolBytesPerEntry; }
-size_t dedup_level_pool_bytes(uint32_t cand_cap) { return (size_t)cand_cap * kLevelPoolBytesPerCand; }
+size_t dedup_level_pool_bytes(const Plan& P, uint32_t cand_cap) {  // per image: pool entries, row tables, (appends, entries) per level
+    const size_t b = (size_t)cand_cap * kLevelPoolBytesPerCand + (size_t)P.dev.ltab_off[P.dev.n_levels] * sizeof(unsigned short) +
+                     2 * kMaxLevels * sizeof(unsigned int);
+    return (b + 255) & ~(size_t)255;
+}
 template <int KG>
 static size_t level_pass_smem(const Plan& P) {
     return (size_t)P.dev.n_levels * KG * sizeof(uint4) + (size_t)P.dev.ltab_off[P.dev.n_levels] * sizeof(unsigned short);
 }
 
 template <int KG>
-static void launch_level_pass(const Launch& L, const Plan& P, const Buffers& B) {
+static void launch_level_pass(const Launch& L, const Plan& P, const Buffers& B, int l0, int l1) {
     // 512-thread blocks (the default 16 levels) may use 128 registers per thread, 1024-thread ones 64
     const size_t smem = level_pass_smem<KG>(P);
+    const size_t slab = dedup_level_pool_bytes(P, L.cand_cap);
+    const int warps = l1 == P.dev.n_levels ? l1 : l1 - l0;  // the part that assigns the final slots has a warp per level
     if (P.dev.n_levels <= 16)
-        k_dedup_levels<KG, 512><<<L.batch, 32 * P.dev.n_levels, smem, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch,
-                                                                                  L.cand_cap, L.kp_cap, B.c_x, B.c_y, B.c_resp, B.c_cls, B.n_cache,
-                                                                                  B.err_flags, B.level_pool, B.keep_flag, B.upper_done);
+        k_dedup_levels<KG, 512><<<L.batch, 32 * warps, smem, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap,
+                                                                         L.kp_cap, B.c_x, B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags,
+                                                                         B.level_pool, B.keep_flag, B.upper_done, slab, l0, l1);
     else
-        k_dedup_levels<KG, 1024><<<L.batch, 32 * P.dev.n_levels, smem, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch,
-                                                                                   L.cand_cap, L.kp_cap, B.c_x, B.c_y, B.c_resp, B.c_cls, B.n_cache,
-                                                                                   B.err_flags, B.level_pool, B.keep_flag, B.upper_done);
+        k_dedup_levels<KG, 1024><<<L.batch, 32 * warps, smem, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap,
+                                                                          L.kp_cap, B.c_x, B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags,
+                                                                          B.level_pool, B.keep_flag, B.upper_done, slab, l0, l1);
 }
 
-int launch_dedup(const Launch& L, const Plan& P, const Buffers& B) {
-    // every image is handled by exactly one of the two kernels launched here (image_fits_*_pass)
+static bool level_pass_enabled(const Plan& P) {
     static const bool single_warp = getenv("AKZ_DEDUP_SINGLE") != nullptr;  // A/B switch: the one-warp-per-image pass
+    return !single_warp && level_pass_smem<16>(P) <= 200 * 1024;
+}
+
+// the first octave's levels go first when the pass is split (they hold ~60 % of the candidates and are known after a
+// quarter of the sub-batch's stencil time at the default 4 x 4 levels)
+int dedup_split_level(const Plan& P) {
+    // Opt-in (AKZ_SPLIT_PASS=1). Measured: the first part's warps share their SMs with sixteen busy stencil warps and crawl
+    // (a single 3840x2160 image: 7.0 ms against 5.6 ms unsplit; 32 of them per step: 1413 against 1394 images/s; a single
+    // 1080p image: 1.73 against 1.70 ms), so the pass stays in one piece by default.
+    static const bool split = getenv("AKZ_SPLIT_PASS") != nullptr;
+    if (!split || !level_pass_enabled(P)) return 0;
+    int l = 1;
+    while (l < P.dev.n_levels && !P.dev.lv[l].new_octave) l++;
+    return l < P.dev.n_levels ? l : 0;
+}
+
+int launch_dedup(const Launch& L, const Plan& P, const Buffers& B, int l0, int l1) {
+    // every image is handled by exactly one of the kernels launched here (image_fits_*_pass)
     static const int groups = getenv("AKZ_DEDUP_GROUPS") ? atoi(getenv("AKZ_DEDUP_GROUPS")) : 8;  // A/B switch: candidates per step
-    const bool levels = !single_warp && level_pass_smem<16>(P) <= 200 * 1024;
+    if (l1 < 0) l1 = P.dev.n_levels;
+    const bool levels = level_pass_enabled(P);
     if (levels && groups == 16) {
-        launch_level_pass<16>(L, P, B);
+        launch_level_pass<16>(L, P, B, l0, l1);
     } else if (levels) {
-        launch_level_pass<8>(L, P, B);
+        launch_level_pass<8>(L, P, B, l0, l1);
     } else {
         k_dedup_smem<<<L.batch, 32, 0, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap, L.kp_cap, B.c_x,
                                                    B.c_y, B.c_resp, B.c_cls, B.n_cache, B.err_flags, B.dedup_pool, B.upper_done);
     }
+    if (l1 != P.dev.n_levels) return 1;  // (only the level pass is ever launched in parts)
     k_dedup<<<L.batch, 32, 0, L.stream>>>(B.plan_dev, B.cand, B.cand_level_count, B.Ldet, L.batch, L.cand_cap, L.kp_cap,
                                            B.c_x, B.c_y, B.c_resp, B.c_cls, B.c_next, B.grid, B.n_cache, B.err_flags, levels ? 1 : 0, B.upper_done);
     return 2;
@@ -1247,14 +1293,15 @@ int launch_finalize(const Launch& L, const Plan& P, const Buffers& B) {
     k_filter_refine<<<g1, 256, 0, L.stream>>>(B.plan_dev, B.Ldet, L.batch, L.kp_cap, B.c_x, B.c_y, B.c_cls, B.n_cache, B.cls_range,
                                               r_x, r_y, B.keep_flag, B.upper_done);
     k_keep_scan<<<L.batch, 1024, 0, L.stream>>>(B.keep_flag, B.n_cache, B.n_kp, L.kp_cap);
-    dim3 g3(16, L.batch);
+    // a single image or a small batch spreads over more, hence shorter, blocks (16 blocks per image fill the GPU from ~20 images)
+    dim3 g3(std::min(128, std::max(16, 148 * 2 / std::max(1, L.batch))), L.batch);
     k_orientation<<<g3, 128, 0, L.stream>>>(B.plan_dev, B.Lx, B.Ly, L.batch, L.kp_cap, r_x, r_y, B.c_resp, B.c_cls, B.keep_flag,
                                             B.n_cache, B.kps, B.err_flags);
     return 4;
 }
 
 int launch_descriptors(const Launch& L, const Plan& P, const Buffers& B) {
-    dim3 g(32, L.batch);
+    dim3 g(std::min(256, std::max(32, 148 * 4 / std::max(1, L.batch))), L.batch);  // small batches: more blocks per image
     if (P.dev.channels == 3 && P.dev.pattern_size == 10)
         k_descriptor<true><<<g, 256, 0, L.stream>>>(B.plan_dev, B.Lt, B.Lx, B.Ly, L.batch, L.kp_cap, B.kps, B.n_kp, B.desc, B.err_flags);
     else

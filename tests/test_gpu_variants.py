@@ -56,7 +56,7 @@ def test_kernel_variants_agree(akz):
     assert all(n > 100 for _h, n in base.values()), base
     for env in ({"AKZ_DET_SMEM": "1"}, {"AKZ_FED_OLD": "1"}, {"AKZ_NO_CONTRAST_FUSION": "1"}, {"AKZ_DETECTOR_TILE": "1"},
                 {"AKZ_FED_MAXT": "8"}, {"AKZ_SERIAL_LANES": "1"}, {"AKZ_DEDUP_SINGLE": "1"}, {"AKZ_NO_RAMP": "1"}, {"AKZ_DET_INLINE": "1"}, {"AKZ_NO_G2_FUSION": "1"},
-                {"AKZ_DEDUP_GROUPS": "16"}, {"AKZ_NO_GRAPH": "1"}, {"AKZ_NO_SHORT_SEGMENTS": "1"}, {"AKZ_FINE_HIST": "1"}, {"AKZ_FINE_HIST_EXACT": "1"}, {"AKZ_DET_WPC": "20"}):
+                {"AKZ_DEDUP_GROUPS": "16"}, {"AKZ_NO_GRAPH": "1"}, {"AKZ_SPLIT_PASS": "1"}, {"AKZ_NO_SHORT_SEGMENTS": "1"}, {"AKZ_FINE_HIST": "1"}, {"AKZ_FINE_HIST_EXACT": "1"}, {"AKZ_DET_WPC": "20"}):
         assert run_variant(env) == base, env
 
 
