@@ -10,6 +10,7 @@ one STEP is one pass over the batch; `value` is whole-job images/s with the u8 i
 the same metric through the reference-facing host-buffer call (akz_extract_batch_u8 on pinned host images: H2D of the
 images and D2H of keypoints + descriptors inside the timed region). Two more legs ride in the same line:
   "extract_4k": configs[3], 3840x2160, 32 images per GPU and step (256 images over 8 GPUs), same fields;
+  "single_image": configs[0]/[1] analogue: one 1080p image per call through the public host API, median wall-clock ms;
   "match":      configs[4] and BASELINE.json's second metric: brute-force Hamming top-2 of 1M x 1M 486-bit descriptors,
                 the database sharded by index over the ranks, per-shard top-2 records all-gathered with NCCL and merged
                 INSIDE the library (akz_match_top2_sharded_device); strong scaling.
@@ -60,6 +61,7 @@ def parse():
     ap.add_argument("--match-n", type=int, default=1 << 20, help="queries = database size of the match leg")
     ap.add_argument("--match-path", default="auto", choices=["auto", "popc", "tensor"], help="matcher kernel (auto = tensor at these sizes)")
     ap.add_argument("--cpu-images", type=int, default=8, help="images in the bounded CPU sample / parity check")
+    ap.add_argument("--single-calls", type=int, default=30, help="calls of the one-image latency measurement (0 = skip)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -606,6 +608,37 @@ def run_match(args):
     return res
 
 
+def run_single_image(args, images, h, w):
+    """configs[0]/[1] analogue: ONE image per call through the public API, host buffer in, keypoints and descriptors in host
+    memory out (wall clock around the call; a one-sub-batch call replays a captured CUDA graph)."""
+    import time
+    import torch
+    import akaze_rust_b200 as A
+    world, rank, local = dist_setup()
+    eng = A.Engine(local, w, h, 1)
+    img = np.ascontiguousarray(images[0])
+    n_kp = 0
+    for _ in range(5):
+        f = eng.extract_u8(img)
+        n_kp = len(f.keypoints)
+        f.release()
+    l0 = eng.launch_count
+    ts = []
+    for _ in range(args.single_calls):
+        t0 = time.perf_counter()
+        f = eng.extract_u8(img)
+        kp, de = f.keypoints, f.descriptors_padded
+        ts.append((time.perf_counter() - t0) * 1e3)
+        f.release()
+    launches = (eng.launch_count - l0) // max(1, args.single_calls)
+    eng.close()
+    torch.cuda.empty_cache()
+    ts.sort()
+    return {"workload": "one %dx%d image per call (extract_features on an image in host memory): host buffer in, keypoints + descriptors in host memory out" % (w, h),
+            "ms_median": ts[len(ts) // 2], "ms_min": ts[0], "calls": args.single_calls, "keypoints": n_kp, "gpu_launches_per_call": int(launches),
+            "timing": "host wall clock around the call"}
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -630,6 +663,8 @@ def main():
     res = {}
     if "extract" in legs:
         res["extract"] = run_extract(args, imgs, H1080, W1080, args.images, full=True)
+    if "extract" in legs and rank == 0 and args.single_calls > 0:
+        res["single_image"] = run_single_image(args, imgs, H1080, W1080)
     if "extract_4k" in legs:
         res["extract_4k"] = run_extract(args, imgs4k, H4K, W4K, args.images_4k, full=False)
     if "match" in legs:
@@ -647,6 +682,8 @@ def main():
                 "dtype": "f32", "data": "synthetic", "config": x["config"], "run": x["run"], "clocks": x["clocks"], "e2e": x["e2e"],
                 "gpu_launches": x["gpu_launches"], "roofline": x["roofline"], "roofline_pipeline": x["roofline_pipeline"],
                 "stages": x["stages"], "cpu_baseline": x["cpu_baseline"], "parity_check": x["parity_check"]}
+        if "single_image" in res:
+            line["single_image"] = res["single_image"]
         if x["parity_check"] and not x["parity_check"]["ok"]:
             failures.append("extract parity_check")
         if "extract_4k" in res:

@@ -19,6 +19,8 @@ try:
     d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
     print("extract: value %.1f e2e %.1f img/s n_gpus %d" % (d["value"], d["e2e"]["value"], d["n_gpus"]), {k: round(v["ms_per_image"], 4) for k, v in d["stages"].items()})
     print("  cpu", d["cpu_baseline"] and round(d["cpu_baseline"]["value"], 3), "parity", d["parity_check"] and (d["parity_check"]["ok"], d["parity_check"]["bit_exact_keypoints"], d["parity_check"]["descriptor_bits_differing"]))
+    if "single_image" in d:
+        print("  single image: %.3f ms median, %.3f min, %d keypoints, %d launches" % (d["single_image"]["ms_median"], d["single_image"]["ms_min"], d["single_image"]["keypoints"], d["single_image"]["gpu_launches_per_call"]))
     if "extract_4k" in d:
         x = d["extract_4k"]; print("  4k: value %.1f e2e %.1f frac %.3f" % (x["value"], x["e2e"]["value"], x["roofline_pipeline"]["frac"]), {k: round(v["ms_per_image"], 4) for k, v in x["stages"].items()})
     if "match" in d:
