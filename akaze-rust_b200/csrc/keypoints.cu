@@ -1201,7 +1201,7 @@ k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plan
 template <int KG, int MAXT>
 static cudaError_t level_pass_attributes() {
     // see init_detector_attributes: the cache pass must not pin a small shared-memory carveout on the SMs it lives on
-    cudaError_t e = cudaFuncSetAttribute(k_dedup_levels<KG, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(k_dedup_levels<KG, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess || getenv("AKZ_NO_CARVEOUT") != nullptr) return e;
     return cudaFuncSetAttribute(k_dedup_levels<KG, MAXT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
 }
@@ -1256,9 +1256,11 @@ static bool level_pass_enabled(const Plan& P) {
 // the first octave's levels go first when the pass is split (they hold ~60 % of the candidates and are known after a
 // quarter of the sub-batch's stencil time at the default 4 x 4 levels)
 int dedup_split_level(const Plan& P) {
-    // Opt-in (AKZ_SPLIT_PASS=1). Measured: the first part's warps share their SMs with sixteen busy stencil warps and crawl
-    // (a single 3840x2160 image: 7.0 ms against 5.6 ms unsplit; 32 of them per step: 1413 against 1394 images/s; a single
-    // 1080p image: 1.73 against 1.70 ms), so the pass stays in one piece by default.
+    // Opt-in (AKZ_SPLIT_PASS=1). Measured: the second octave's levels, not the first's, are the critical path of the pass (they
+    // scan more rows of the level before them per candidate), so the part that has to wait for the last detector is nearly as
+    // long as the whole pass and no longer overlaps the first octave's levels: a single 3840x2160 image takes 7.0 ms against
+    // 5.6 ms unsplit (the same with the first part alone on its SM), 32 of them per step run at 1413 against 1394 images/s, a
+    // single 1080p image 1.73 against 1.70 ms. The pass stays in one piece by default.
     static const bool split = getenv("AKZ_SPLIT_PASS") != nullptr;
     if (!split || !level_pass_enabled(P)) return 0;
     int l = 1;
