@@ -454,7 +454,7 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
     // the image's slab, the part that ends at the last level reloads them and assigns the final slots for every level.
     extern __shared__ uint4 s_dyn[];  // per level KG step records (float4), then the row tables (u16, level l at ltab_off[l])
     __shared__ volatile int s_progress[kMaxLevels];
-    __shared__ unsigned int s_appends[kMaxLevels], s_base[kMaxLevels + 1];
+    __shared__ unsigned int s_appends[kMaxLevels], s_entries[kMaxLevels], s_base[kMaxLevels + 1];
     __shared__ int s_ok;
     const unsigned int FULL = 0xffffffffu;
     const int img = blockIdx.x;
@@ -688,6 +688,7 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
     __threadfence_block();
     if (lane == 0) {
         s_appends[L] = n_app;
+        s_entries[L] = cnt;
         s_progress[L] = 0x7fffffff;  // level finished
     }
     if (!final_part) {  // leave the table and the counts for the part that follows
@@ -721,43 +722,50 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
     // of it -- the class L+1 entries are exactly the live entries of pool L+1, and its row table is still in shared memory,
     // so the scan over the whole class (quadratic in the keypoint count; 13 x the time for 4.8 x the keypoints at 3840x2160)
     // becomes a look at the rows the circle touches.
+    // All threads of the block share the work level by level (the busiest level has ~10 x the entries of the quietest).
     keep_flag += (size_t)img * kp_cap;
-    const bool has_up = L + 1 < nl;
-    const int Lu = has_up ? L + 1 : L;
-    const LevelDev& uv = plan->lv[Lu];
-    const unsigned short* t_up = s_rows + plan->ltab_off[Lu];
-    const unsigned int ubeg = lo[Lu];
-    const float u_hr = uv.half_ratio_m1, u_inv = 1.0f / uv.ratio;
     constexpr unsigned int kIdxMask = (1u << kKeyShift) - 1u;
-    for (unsigned int e = lane; e < cnt; e += 32) {
-        const float4 rec = pool[beg + e];
-        const unsigned int key = __float_as_uint(rec.w);
-        if (key == kDeadKey) continue;
-        const unsigned int slot = s_base[key >> kKeyShift] + (key & kIdxMask);
-        const float xi = rec.x, yi = rec.y;
-        bool repeated = false;
-        if (has_up) {
-            const int u_lo = max(0, (int)ceilf((yi - reach - u_hr) * u_inv));
-            const int u_hi = min(uv.h - 1, (int)floorf((yi + reach - u_hr) * u_inv));
-            const unsigned int j1 = u_lo <= u_hi ? ubeg + t_up[u_hi + 1] : 0u;
-            for (unsigned int j = ubeg + t_up[u_lo]; j < j1; j++) {
-                const float4 up = pool[j];
-                const unsigned int ukey = __float_as_uint(up.w);
-                if (ukey != kDeadKey && s_base[ukey >> kKeyShift] + (ukey & kIdxMask) >= slot) {  // :115 scans slots j >= i
-                    const float dx = xi - up.x, dy = yi - up.y;
-                    const float dist = dx * dx + dy * dy;
-                    if (dist <= size_sq) {
-                        repeated = true;
-                        break;
+    for (int l = 0; l < nl; l++) {
+        const LevelDev& wl = plan->lv[l];
+        const bool has_up = l + 1 < nl;
+        const int lu = has_up ? l + 1 : l;
+        const LevelDev& uv = plan->lv[lu];
+        const unsigned short* t_up = s_rows + plan->ltab_off[lu];
+        const unsigned int lbeg = lo[l], ubeg = lo[lu], n_l = s_entries[l];
+        const float l_size_sq = wl.size_sq, l_reach = wl.kp_size + 0.01f;
+        const float u_hr = uv.half_ratio_m1, u_inv = 1.0f / uv.ratio;
+        for (unsigned int e = threadIdx.x; e < n_l; e += blockDim.x) {
+            const float4 rec = pool[lbeg + e];
+            const unsigned int key = __float_as_uint(rec.w);
+            if (key == kDeadKey) continue;
+            const unsigned int slot = s_base[key >> kKeyShift] + (key & kIdxMask);
+            const float xi = rec.x, yi = rec.y;
+            bool repeated = false;
+            if (has_up) {
+                const int u_lo = max(0, (int)ceilf((yi - l_reach - u_hr) * u_inv));
+                const int u_hi = min(uv.h - 1, (int)floorf((yi + l_reach - u_hr) * u_inv));
+                const unsigned int j0 = u_lo <= u_hi ? ubeg + t_up[u_lo] : 0u;
+                const unsigned int j1 = u_lo <= u_hi ? ubeg + t_up[u_hi + 1] : 0u;
+                for (unsigned int j = j0; j < j1 && !repeated; j += 4) {
+                    float4 up[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) up[u] = pool[min(j + u, j1 - 1u)];  // (past the end: the last record once more)
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const unsigned int ukey = __float_as_uint(up[u].w);
+                        const float dx = xi - up[u].x, dy = yi - up[u].y;
+                        const float dist = dx * dx + dy * dy;
+                        // :115 scans the slots j >= i
+                        if (ukey != kDeadKey && dist <= l_size_sq && s_base[ukey >> kKeyShift] + (ukey & kIdxMask) >= slot) repeated = true;
                     }
                 }
             }
+            c_x[slot] = xi;
+            c_y[slot] = yi;
+            c_resp[slot] = rec.z;
+            c_cls[slot] = l;
+            keep_flag[slot] = repeated ? 0u : 1u;
         }
-        c_x[slot] = xi;
-        c_y[slot] = yi;
-        c_resp[slot] = rec.z;
-        c_cls[slot] = L;
-        keep_flag[slot] = repeated ? 0u : 1u;
     }
 }
 
