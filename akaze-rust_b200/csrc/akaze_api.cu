@@ -401,6 +401,8 @@ struct akz_context {
     int comm_rank = 0, comm_size = 1;
     void* m_gather = nullptr;
     size_t m_gather_cap = 0;
+    void* m_stage = nullptr;  // host descriptor rows as uploaded, before they are repacked to 64-byte rows
+    size_t m_stage_cap = 0;
 };
 
 // live contexts by id: a handle that outlives its context must fail cleanly instead of touching freed memory
@@ -1136,6 +1138,7 @@ void akz_destroy(akz_context* c) {
     cudaSetDevice(c->device);
     if (c->comm) nccl_dyn::api().CommDestroy(c->comm);
     cudaFree(c->m_gather);
+    cudaFree(c->m_stage);
     cudaStreamSynchronize(c->stream);
     cudaStreamSynchronize(c->stream_kp);
     free_buffers(c);
@@ -1389,8 +1392,10 @@ int akz_match_top2_device(akz_context* c, const void* d_q, uint64_t nq, const vo
     LOCK(c);
     if (ndb > 0xffffffffull || nq > 0xffffffffull) return fail(AKZ_ERR_CAPACITY, "more than 2^32 descriptors");
     CK(cudaSetDevice(c->device));
-    // tensor-core path (matcher_tc.cu) unless the problem is too small to amortise the 64 KB operand tiles
-    const bool tensor = ndb > 0 && (c->match_path == AKZ_MATCH_TENSOR || (c->match_path == AKZ_MATCH_AUTO && nq * ndb >= (1ull << 20)));
+    // tensor-core path (matcher_tc.cu) unless the problem is tiny
+    // (measured through the host call, tools/match_latency.py: equal at 32 x 32, tensor 0.06 vs popc 0.10 ms at 128 x 128, 0.14 vs 0.40 ms at
+    // the 7 395 x 5 629 descriptors of the reference's test images)
+    const bool tensor = ndb > 0 && (c->match_path == AKZ_MATCH_TENSOR || (c->match_path == AKZ_MATCH_AUTO && nq * ndb >= (1ull << 12)));
     const int parts = tensor ? match_tc_parts(nq, ndb) : match_parts(nq, ndb);
     akz_top2* dst = (akz_top2*)d_out;
     if (parts > 1) {
@@ -1430,8 +1435,14 @@ static int upload_padded(akz_context* c, const uint8_t* src, uint64_t n, uint32_
     if (stride == (size_t)kDescStride && desc_len == (uint32_t)kDescStride) {
         CK(cudaMemcpyAsync(*dbuf, src, (size_t)n * kDescStride, cudaMemcpyHostToDevice, c->stream));
     } else {
-        CK(cudaMemsetAsync(*dbuf, 0, (size_t)n * kDescStride, c->stream));
-        CK(cudaMemcpy2DAsync(*dbuf, kDescStride, src, stride, desc_len, n, cudaMemcpyHostToDevice, c->stream));
+        // One linear copy of the rows as they lie in host memory, repacked on the device. (A 2-D copy of 61-byte rows moves
+        // them one DMA descriptor each: 3.7 ms for the 7 395 x 5 629 descriptors of the reference's two test images, against
+        // 0.1 ms for the match itself.)
+        const size_t bytes = (size_t)(n - 1) * stride + desc_len;
+        rc = grow(&c->m_stage, &c->m_stage_cap, bytes);
+        if (rc != AKZ_OK) return rc;
+        CK(cudaMemcpyAsync(c->m_stage, src, bytes, cudaMemcpyHostToDevice, c->stream));
+        c->launches += launch_repack_rows(c->stream, (const uint8_t*)c->m_stage, stride, desc_len, n, (uint8_t*)*dbuf);
     }
     return AKZ_OK;
 }

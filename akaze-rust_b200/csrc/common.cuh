@@ -182,6 +182,7 @@ int match_parts(uint64_t nq, uint64_t ndb);  // how many database parts the grid
 int launch_match_top2(cudaStream_t s, const uint8_t* d_q, uint64_t nq, const uint8_t* d_db, uint64_t ndb,
                       uint32_t db_index_base, akz_top2* d_out, int n_parts);
 int launch_merge_top2(cudaStream_t s, const akz_top2* d_parts, uint32_t n_parts, uint64_t nq, akz_top2* d_out);
+int launch_repack_rows(cudaStream_t s, const uint8_t* d_src, size_t stride, uint32_t desc_len, uint64_t n, uint8_t* d_dst);
 // matcher_tc.cu (tcgen05 int8 path)
 cudaError_t init_matcher_tc_attributes();
 size_t match_tc_query_image_bytes(uint64_t nq);

@@ -136,6 +136,27 @@ int launch_match_top2(cudaStream_t s, const uint8_t* d_q, uint64_t nq, const uin
     return 1;
 }
 
+// rows of `stride` bytes with `desc_len` valid ones -> rows of 64 bytes, zero padded (one thread per 4 output bytes)
+__global__ void k_repack_rows(const uint8_t* __restrict__ src, size_t stride, uint32_t desc_len, uint64_t n, uint32_t* __restrict__ dst) {
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * 16) return;
+    const uint64_t row = t >> 4;
+    const uint32_t col = (uint32_t)(t & 15) * 4;
+    const uint8_t* r = src + row * stride;
+    uint32_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 4; b++)
+        if (col + b < desc_len) v |= (uint32_t)r[col + b] << (8 * b);
+    dst[t] = v;
+}
+
+int launch_repack_rows(cudaStream_t s, const uint8_t* d_src, size_t stride, uint32_t desc_len, uint64_t n, uint8_t* d_dst) {
+    if (n == 0) return 0;
+    const uint64_t threads = n * 16;
+    k_repack_rows<<<(unsigned int)((threads + 255) / 256), 256, 0, s>>>(d_src, stride, desc_len, n, reinterpret_cast<uint32_t*>(d_dst));
+    return 1;
+}
+
 int launch_merge_top2(cudaStream_t s, const akz_top2* d_parts, uint32_t n_parts, uint64_t nq, akz_top2* d_out) {
     if (nq == 0) return 0;
     k_merge_top2<<<(unsigned int)((nq + 255) / 256), 256, 0, s>>>(d_parts, n_parts, nq, d_out);

@@ -133,7 +133,7 @@ int akz_context_set_limits(akz_context *ctx, uint32_t max_candidates, uint32_t m
  * Default: up to 256, chosen so that both lanes fit in half of the free device memory; memory per in-flight image is about 0.2 GB at 1080p. Environment override: AKZ_SUB_BATCH. */
 int akz_context_set_sub_batch(akz_context *ctx, uint32_t images);
 
-/* Which kernel akz_match_top2* runs: AUTO picks the tcgen05 int8 path (matcher_tc.cu) for nq*ndb >= 2^20 pairs
+/* Which kernel akz_match_top2* runs: AUTO picks the tcgen05 int8 path (matcher_tc.cu) for nq*ndb >= 2^12 pairs
  * and the integer-popc path (matcher.cu) below that; both are bit-exact. */
 enum akz_match_path { AKZ_MATCH_AUTO = 0, AKZ_MATCH_POPC = 1, AKZ_MATCH_TENSOR = 2 };
 int akz_context_set_match_path(akz_context *ctx, int path);
