@@ -165,6 +165,11 @@ int launch_fed(const Launch& L, const Plan& P, const Buffers& B, int level);
 cudaError_t init_detector_attributes();
 cudaError_t init_scale_space_attributes();
 int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level);
+// shortest segment the streaming kernels cut a small grid into (AKZ_MIN_SEGMENT overrides, for profiling)
+inline int min_segment_rows() {
+    static const int v = getenv("AKZ_MIN_SEGMENT") ? std::max(2, atoi(getenv("AKZ_MIN_SEGMENT")) & ~1) : 8;
+    return v;
+}
 int launch_compact(const Launch& L, const Plan& P, const Buffers& B, int l0 = 0, int l1 = -1);  // levels [l0, l1), -1 = all
 // keypoints.cu
 cudaError_t init_keypoint_attributes();

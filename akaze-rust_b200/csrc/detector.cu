@@ -1112,7 +1112,7 @@ int launch_detector(const Launch& L, const Plan& P, const Buffers& B, int level)
             // a single image or a small batch: down to 8-row segments (2-3 x the rows per segment with their warm-up, but the
             // kernel is as long as ONE warp's walk) while the grid is still short of one wave
             static const bool no_short = getenv("AKZ_NO_SHORT_SEGMENTS") != nullptr;  // A/B switch
-            while (!no_short && RL > 8 && warps(RL) < 148LL * 16) RL >>= 1;
+            while (!no_short && RL > min_segment_rows() && warps(RL) < 148LL * 16) RL >>= 1;
         }
         if (rl_env > 0) RL = rl_env;
         // equal-height segments (the last one used to take the remainder: 312 rows against 256 at 1080p, and a CTA of the
