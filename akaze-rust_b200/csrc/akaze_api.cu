@@ -267,7 +267,7 @@ std::string build_plan(uint32_t w, uint32_t h, const akz_config& cfg, Plan* P) {
     // cache-pass pools: room for the candidates of the busiest level (a photo-like 1080p frame has ~2 k per level, a
     // 3840x2160 one ~10 k); images beyond it take the global-memory pass
     D.pool_cap = (int)std::min<uint64_t>(64512, std::max<uint64_t>(4096, (((uint64_t)w * h / 384) + 1023) & ~1023ull));
-    // level-pipelined cache pass: one row table per level in shared memory (a 1080p frame: 16 KB, 3840x2160: 32 KB)
+    // level-pipelined cache pass: one row table per level in shared memory (a 1080p frame: 32 KB, 3840x2160: 65 KB)
     D.ltab_off[0] = 0;
     for (int l = 0; l < nl; l++) D.ltab_off[l + 1] = D.ltab_off[l] + ((D.lv[l].h + 2 + 7) & ~7);
     return "";

@@ -56,7 +56,7 @@ struct PlanDev {
     int grid_shift;        // dedup hash grid: cell = 1<<grid_shift full-resolution pixels
     int grid_w, grid_h;
     int pool_cap;          // entries per class-parity pool of the single-warp cache pass (per image)
-    // level-pipelined cache pass: one row table of u16 pool indices per level in shared memory, level l (lv[l].h + 2
+    // level-pipelined cache pass: one row table of u32 pool indices per level in shared memory, level l (lv[l].h + 2
     // entries) at ltab_off[l]; ltab_off[n_levels] = entries in total
     int ltab_off[kMaxLevels + 1];
     LevelDev lv[kMaxLevels];

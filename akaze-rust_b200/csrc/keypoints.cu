@@ -428,7 +428,8 @@ k_dedup_smem(const PlanDev* __restrict__ plan, const unsigned int* __restrict__ 
 // ------------------------------------------------------------------------------------------------
 constexpr unsigned int kDeadKey = 0xffffffffu;
 constexpr int kKeyShift = 20;               // key = (level of the append << 20) | index of the append inside its level
-constexpr unsigned int kMaxLevelCands = 65534;  // row tables hold u16 indices
+constexpr unsigned int kMaxLevelCands = (1u << kKeyShift) - 1u;  // the index field of a key
+typedef unsigned int row_t;  // row-table entry (u16 would halve the tables and send levels beyond 65 534 candidates to k_dedup)
 
 // (the levels [0, n): a first part of the pass only knows the offsets of its own levels)
 __device__ __forceinline__ bool image_fits_level_pass(const PlanDev* plan, const unsigned int* lo, int n) {
@@ -452,7 +453,7 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
     // behind (a single image, the last of a call) runs it in two: the first octave as soon as its detectors are through, next
     // to the stencil kernels of the other octaves, the rest at the end. The first part leaves its row tables and counts in
     // the image's slab, the part that ends at the last level reloads them and assigns the final slots for every level.
-    extern __shared__ uint4 s_dyn[];  // per level KG step records (float4), then the row tables (u16, level l at ltab_off[l])
+    extern __shared__ uint4 s_dyn[];  // per level KG step records (float4), then the row tables (u32, level l at ltab_off[l])
     __shared__ volatile int s_progress[kMaxLevels];
     __shared__ unsigned int s_appends[kMaxLevels], s_entries[kMaxLevels], s_base[kMaxLevels + 1];
     __shared__ int s_ok;
@@ -462,12 +463,12 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
     const bool final_part = l1 == nl;  // (then the block has a warp for every level, else one for each of [l0, l1))
     const int lane = threadIdx.x & 31, L = (threadIdx.x >> 5) + (final_part ? 0 : l0);  // one warp per level
     float4* s_step = reinterpret_cast<float4*>(s_dyn) + (threadIdx.x >> 5) * KG;
-    unsigned short* s_rows = reinterpret_cast<unsigned short*>(s_dyn + nl * KG);
+    row_t* s_rows = reinterpret_cast<row_t*>(s_dyn + nl * KG);
     const unsigned int* cl = cand + (size_t)img * cand_cap;
     const unsigned int* lo = level_off + (size_t)img * (kMaxLevels + 1);
     unsigned char* slab = pools + (size_t)img * slab_bytes;  // pool entries, then the row tables, then (appends, entries) per level
     float4* pool = reinterpret_cast<float4*>(slab);
-    unsigned short* g_rows = reinterpret_cast<unsigned short*>(slab + (size_t)cand_cap * kLevelPoolBytesPerCand);
+    row_t* g_rows = reinterpret_cast<row_t*>(slab + (size_t)cand_cap * kLevelPoolBytesPerCand);
     unsigned int* g_meta = reinterpret_cast<unsigned int*>(g_rows + plan->ltab_off[nl]);
     if (threadIdx.x == 0) s_ok = !(err_flags[img] & kErrCandOverflow) && image_fits_level_pass(plan, lo, l1);
     if (threadIdx.x < kMaxLevels) {
@@ -476,7 +477,7 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
     }
     for (int i = threadIdx.x; i < plan->ltab_off[l0]; i += blockDim.x) s_rows[i] = g_rows[i];
     __syncthreads();
-    if (!s_ok) {  // candidate overflow: nothing to do; a level beyond the u16 tables: k_dedup takes the image
+    if (!s_ok) {  // candidate overflow: nothing to do; a level with more candidates than a key's index field holds: k_dedup takes the image
         if (threadIdx.x == 0 && final_part && (err_flags[img] & kErrCandOverflow)) {
             n_cache[img] = 0;
             upper_done[img] = 0;
@@ -491,8 +492,8 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
     const LevelDev& lv = plan->lv[L];
     const int Lp = L > 0 ? L - 1 : 0;
     const LevelDev& pv = plan->lv[Lp];
-    unsigned short* t_cur = s_rows + plan->ltab_off[L];        // t_cur[r] = entries of this pool above row r
-    const unsigned short* t_prv = s_rows + plan->ltab_off[Lp];
+    row_t* t_cur = s_rows + plan->ltab_off[L];        // t_cur[r] = entries of this pool above row r
+    const row_t* t_prv = s_rows + plan->ltab_off[Lp];
     const unsigned int beg = lo[L], end = lo[L + 1];
     const unsigned int pbeg = L > 0 ? lo[L - 1] : 0u;  // pool base of level L-1
     const float ratio = lv.ratio, size = lv.kp_size, size_sq = lv.size_sq, hr = lv.half_ratio_m1;
@@ -549,7 +550,7 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
             // step's last candidate.
             const int r0 = __shfl_sync(FULL, my_py, k0);
 #pragma unroll 1
-            for (int r = filled + 1 + lane; r <= r0; r += 32) t_cur[r] = (unsigned short)cnt;
+            for (int r = filled + 1 + lane; r <= r0; r += 32) t_cur[r] = cnt;
             filled = r0;
             if (L > 0) {
                 const int rl = __shfl_sync(FULL, my_py, min(k0 + KG - 1, n_here - 1));
@@ -656,7 +657,7 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
             if (commits) {
                 if (grp > 0) {
 #pragma unroll 1
-                    for (int r = py_before + 1; r <= py; r++) t_cur[r] = (unsigned short)e;  // a new row starts here
+                    for (int r = py_before + 1; r <= py; r++) t_cur[r] = e;  // a new row starts here
                 }
                 if (act != 0) {
                     const unsigned int key = (act == 1) ? (((unsigned int)L << kKeyShift) | (n_app + __popc(amask & lt))) : best;
@@ -674,7 +675,7 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
     }
     if (walks) {
 #pragma unroll 1
-        for (int r = filled + 1 + lane; r <= lv.h; r += 32) t_cur[r] = (unsigned short)cnt;
+        for (int r = filled + 1 + lane; r <= lv.h; r += 32) t_cur[r] = cnt;
     }
 #ifdef AKZ_DEDUP_STATS
     {
@@ -730,7 +731,7 @@ k_dedup_levels(const PlanDev* __restrict__ plan, const unsigned int* __restrict_
         const bool has_up = l + 1 < nl;
         const int lu = has_up ? l + 1 : l;
         const LevelDev& uv = plan->lv[lu];
-        const unsigned short* t_up = s_rows + plan->ltab_off[lu];
+        const row_t* t_up = s_rows + plan->ltab_off[lu];
         const unsigned int lbeg = lo[l], ubeg = lo[lu], n_l = s_entries[l];
         const float l_size_sq = wl.size_sq, l_reach = wl.kp_size + 0.01f;
         const float u_hr = uv.half_ratio_m1, u_inv = 1.0f / uv.ratio;
@@ -1231,13 +1232,13 @@ cudaError_t init_keypoint_attributes() {
 
 size_t dedup_pool_bytes(const Plan& P) { return (size_t)P.dev.pool_cap * kPoolBytesPerEntry; }
 size_t dedup_level_pool_bytes(const Plan& P, uint32_t cand_cap) {  // per image: pool entries, row tables, (appends, entries) per level
-    const size_t b = (size_t)cand_cap * kLevelPoolBytesPerCand + (size_t)P.dev.ltab_off[P.dev.n_levels] * sizeof(unsigned short) +
+    const size_t b = (size_t)cand_cap * kLevelPoolBytesPerCand + (size_t)P.dev.ltab_off[P.dev.n_levels] * sizeof(unsigned int) +
                      2 * kMaxLevels * sizeof(unsigned int);
     return (b + 255) & ~(size_t)255;
 }
 template <int KG>
 static size_t level_pass_smem(const Plan& P) {
-    return (size_t)P.dev.n_levels * KG * sizeof(uint4) + (size_t)P.dev.ltab_off[P.dev.n_levels] * sizeof(unsigned short);
+    return (size_t)P.dev.n_levels * KG * sizeof(uint4) + (size_t)P.dev.ltab_off[P.dev.n_levels] * sizeof(unsigned int);
 }
 
 template <int KG>

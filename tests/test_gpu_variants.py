@@ -81,3 +81,34 @@ def test_default_path_matches_oracle_4k(akz, oracle):
     assert bits <= 1e-4 * ref.descriptors.size * 8, bits
     f.release()
     eng.close()
+
+
+def test_dense_image_beyond_65534_candidates_per_level(akz):
+    """A noise image whose busiest level has more candidates than a u16 index holds: the level-pipelined cache pass (u32 row
+    tables) and the one-warp-per-image pass produce the same keypoints and descriptors."""
+    out = {}
+    for env in ({}, {"AKZ_DEDUP_SINGLE": "1"}):
+        e = dict(os.environ)
+        e.update(env)
+        code = r'''
+import sys, json, hashlib
+sys.path.insert(0, %r)
+import numpy as np, importlib
+A = importlib.import_module("akaze-rust_b200")
+img = np.random.default_rng(5).integers(0, 256, (3000, 4096), dtype=np.uint8)
+eng = A.Engine(0, 4096, 3000, 1, max_candidates=1 << 21, max_keypoints=1 << 20)
+f = eng.extract_u8(img)
+h = hashlib.sha256(f.keypoints.tobytes() + f.descriptors_padded.tobytes()).hexdigest()
+busiest = 0
+for level in (1, 2, 3):  # strict 4-neighbour maxima above the detector threshold, as the detector counts them (interior only)
+    d = f.evolution(level, "Ldet")
+    c = d[1:-1, 1:-1]
+    m = (c > 0.001) & (c > d[:-2, 1:-1]) & (c > d[2:, 1:-1]) & (c > d[1:-1, :-2]) & (c > d[1:-1, 2:])
+    busiest = max(busiest, int(m.sum()))
+print(json.dumps([h, int(f.count), int(f.num_candidates), busiest]))
+''' % ROOT
+        r = subprocess.run([sys.executable, "-c", code], env=e, capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stderr[-2000:]
+        out[bool(env)] = json.loads(r.stdout.strip().splitlines()[-1])
+    assert out[False] == out[True], out
+    assert out[False][3] > 70000, out
