@@ -1025,7 +1025,6 @@ k_orientation(const PlanDev* __restrict__ plan, const float* __restrict__ lx_pla
 constexpr int kDescWarps = 8;
 constexpr int kDescM = 21;          // lattice edge for pattern 10 (3 cells x 7)
 constexpr int kDescCS = 463;        // channel stride in shared memory (>= 21*21; chosen for few bank conflicts in phase 2)
-constexpr int kDescBits = 486;      // (6 + 36 + 120) * 3
 
 // sums of one grid level: NC x NC cells of STEP x STEP lattice points, lane t owns (cell, channel) = (t / nch, t % nch)
 template <int STEP, int NC>
@@ -1076,7 +1075,6 @@ k_descriptor(const PlanDev* __restrict__ plan, const float* __restrict__ lt_plan
     const float pf = (float)pattern;
     const int st0 = (int)ceilf(pf * 1.0f), st1 = (int)ceilf(pf * (2.0f / 3.0f)), st2 = (int)ceilf(pf * (1.0f / 2.0f));
     const int M = DEF ? kDescM : max(2 * st0, max(3 * st1, 4 * st2));  // <= kDescM (validated on the host)
-    const int MM = M * M;
     const int nbits = 162 * nch;
     {   // bit -> (i, j) table, identical for every keypoint
         for (int d = threadIdx.x; d < 512; d += blockDim.x) {
