@@ -6,7 +6,7 @@ what=${*:-extract match}
 mkdir -p gpurun_out
 has() { [[ " $what " == *" $1 "* ]]; }
 if has extract; then
-  AKZ_NO_RAMP=1 timeout 1200 ncu --set full --clock-control none -k regex:k_ -c 140 -o /tmp/${tag}_full python tools/profile_run.py --images 64 --unique 8 > gpurun_out/${tag}_full.log 2>&1
+  AKZ_NO_RAMP=1 AKZ_NO_GRAPH=1 timeout 1200 ncu --set full --clock-control none -k regex:k_ -c 140 -o /tmp/${tag}_full python tools/profile_run.py --images 64 --unique 8 > gpurun_out/${tag}_full.log 2>&1
   echo "ncu extract exit $?"
   ncu -i /tmp/${tag}_full.ncu-rep --page raw --csv > gpurun_out/${tag}_full_raw.csv 2>> gpurun_out/${tag}_full.log
   python tools/ncu_rows.py gpurun_out/${tag}_full_raw.csv > gpurun_out/${tag}_ncu_fullload.txt; head -3 gpurun_out/${tag}_ncu_fullload.txt | cut -c1-250
