@@ -373,9 +373,13 @@ struct akz_context {
                    kp_cap == o.kp_cap && is_u8 == o.is_u8;
         }
     };
-    cudaGraphExec_t graph_exec = nullptr;
-    GraphKey graph_key;
-    int graph_launches = 0;
+    struct CachedGraph {
+        GraphKey key;
+        cudaGraphExec_t exec = nullptr;
+        int launches = 0;
+        uint64_t last_use = 0;
+    };
+    std::vector<CachedGraph> graphs;  // a few of them, least recently used out first: callers that rotate input buffers
     uint64_t graph_replays = 0;
     std::vector<std::pair<uint32_t, uint32_t>> sched;  // (first image, count) of every sub-batch of the current call
     // per-stage timing
@@ -889,9 +893,10 @@ static int issue_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_
     return AKZ_OK;
 }
 
-static void drop_graph(akz_context* c) {
-    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
-    c->graph_exec = nullptr;
+static void drop_graphs(akz_context* c) {
+    for (auto& g : c->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    c->graphs.clear();
 }
 
 static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8, size_t in_stride,
@@ -921,8 +926,19 @@ static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8
     key.cand_cap = c->cand_cap;
     key.kp_cap = c->kp_cap;
     key.is_u8 = is_u8;
-    if (!c->graph_exec || !(key == c->graph_key)) {
-        drop_graph(c);
+    constexpr size_t kMaxGraphs = 4;
+    akz_context::CachedGraph* hit = nullptr;
+    for (auto& g : c->graphs)
+        if (g.key == key) hit = &g;
+    if (!hit) {
+        if (c->graphs.size() && !(c->graphs[0].key.alloc_epoch == key.alloc_epoch)) drop_graphs(c);  // buffers moved: all are stale
+        if (c->graphs.size() >= kMaxGraphs) {
+            size_t lru = 0;
+            for (size_t i = 1; i < c->graphs.size(); i++)
+                if (c->graphs[i].last_use < c->graphs[lru].last_use) lru = i;
+            cudaGraphExecDestroy(c->graphs[lru].exec);
+            c->graphs.erase(c->graphs.begin() + lru);
+        }
         CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed));
         int rc = issue_pipeline(c, n, d_in, is_u8, in_stride, nullptr, true, &k);
         cudaGraph_t g = nullptr;
@@ -932,17 +948,19 @@ static int run_pipeline(akz_context* c, uint32_t n, const void* d_in, bool is_u8
             return rc;
         }
         CK(e);
-        e = cudaGraphInstantiate(&c->graph_exec, g, 0);
+        akz_context::CachedGraph cg;
+        e = cudaGraphInstantiate(&cg.exec, g, 0);
         cudaGraphDestroy(g);
-        if (e != cudaSuccess) c->graph_exec = nullptr;
         CK(e);
-        c->graph_key = key;
-        c->graph_launches = k;
+        cg.key = key;
+        cg.launches = k;
+        c->graphs.push_back(cg);
+        hit = &c->graphs.back();
     }
-    CK(cudaGraphLaunch(c->graph_exec, c->stream));
+    hit->last_use = ++c->graph_replays;
+    CK(cudaGraphLaunch(hit->exec, c->stream));
     CK(cudaEventRecord(c->ev_stats[0], c->stream));  // what the host waits for before it reads the statistics
-    c->graph_replays++;
-    c->launches += (uint64_t)c->graph_launches;
+    c->launches += (uint64_t)hit->launches;
     return AKZ_OK;
 }
 
@@ -1152,7 +1170,7 @@ void akz_destroy(akz_context* c) {
             if (c->lane[l].ev_det[i]) cudaEventDestroy(c->lane[l].ev_det[i]);
         }
     }
-    drop_graph(c);
+    drop_graphs(c);
     cudaStreamDestroy(c->stream_kp);
     cudaStreamSynchronize(c->stream_det);
     cudaStreamDestroy(c->stream_det);

@@ -214,3 +214,32 @@ def test_cli_debug_dir_on_the_engine(akz, tmp_path):
     assert "Lt_00.npy" in names and "keypoints.png" in names
     png = np.asarray(Image.open(tmp_path / "dbg" / "Lt_00000..png"))
     assert png.shape == img.shape and png.min() == 0 and png.max() == 255  # normalised to the full range
+
+
+def test_device_inputs_in_rotating_buffers(akz):
+    """akz_extract_batch_u8_device on a caller that rotates three device buffers (one-sub-batch calls replay cached CUDA graphs,
+    keyed by the input pointer among other things): every call returns what the host-buffer call returns for the same images."""
+    import ctypes
+    import torch
+    h, w, n = 360, 480, 2
+    imgs = [np.stack([R.synthetic_image(h, w, seed=40 + 2 * b + i) for i in range(n)]) for b in range(3)]
+    eng = akz.Engine(0, w, h, n)
+    want = []
+    for b in range(3):
+        fs = eng.extract_batch_u8(imgs[b])
+        want.append([(f.keypoints.copy(), f.descriptors_padded.copy()) for f in fs])
+    bufs = [torch.from_numpy(imgs[b]).cuda() for b in range(3)]
+    rt = ctypes.CDLL("libcudart.so.12")
+    for rnd in range(3):  # every buffer is met again after the other two
+        for b in (0, 1, 2, 1):
+            counts = eng.extract_batch_u8_device(bufs[b].data_ptr(), n, w, h)
+            d_kp, d_desc, cap = eng.device_results()
+            for i in range(n):
+                c = int(counts[i])
+                assert c == len(want[b][i][0]) > 50
+                kp = np.zeros(c, akz.KEYPOINT_DTYPE)
+                de = np.zeros((c, 64), np.uint8)
+                assert rt.cudaMemcpy(ctypes.c_void_p(kp.ctypes.data), ctypes.c_void_p(d_kp + i * cap * kp.itemsize), ctypes.c_size_t(kp.nbytes), 2) == 0
+                assert rt.cudaMemcpy(ctypes.c_void_p(de.ctypes.data), ctypes.c_void_p(d_desc + i * cap * 64), ctypes.c_size_t(de.nbytes), 2) == 0
+                assert kp.tobytes() == want[b][i][0].tobytes() and np.array_equal(de, want[b][i][1]), (rnd, b, i)
+    eng.close()
