@@ -643,6 +643,26 @@ def main():
     args = parse()
     if args.impl == "reference":
         return run_reference(args)
+    # stdout carries the ONE JSON line and nothing else: whatever a library prints to file descriptor 1 on the way (NCCL's
+    # "NCCL version ..." banner at the first communicator, for one) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line, failures = run_all(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if line is not None:
+        print(json.dumps(line))
+        sys.stdout.flush()
+    if failures:
+        sys.stderr.write("PARITY FAILED: %s\n" % ", ".join(failures))
+        sys.exit(1)
+
+
+def run_all(args):
     legs = [x for x in args.legs.split(",") if x]
     if args.workload == "match":
         legs = ["match"]
@@ -673,7 +693,7 @@ def main():
         import torch.distributed as dist
         dist.destroy_process_group()
     if rank != 0:
-        return
+        return None, []
     failures = []
     if "extract" in res:
         x = res["extract"]
@@ -706,10 +726,7 @@ def main():
             failures.append("match parity_check")
         if not res["match"]["ranks_agree"]:
             failures.append("match: ranks disagree on the merged result")
-    print(json.dumps(line))
-    if failures:
-        sys.stderr.write("PARITY FAILED: %s\n" % ", ".join(failures))
-        sys.exit(1)
+    return line, failures
 
 
 if __name__ == "__main__":
