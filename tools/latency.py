@@ -20,6 +20,7 @@ def main():
     ap.add_argument("--sizes", default="1080x1920,2160x3840,600x800")
     ap.add_argument("--reps", type=int, default=30)
     ap.add_argument("--batch", type=int, default=1)
+    ap.add_argument("--pinned", action="store_true", help="the input images in page-locked host memory (torch)")
     args = ap.parse_args()
     ak = importlib.import_module("akaze-rust_b200")
     from np_restatement import natural_image
@@ -27,6 +28,10 @@ def main():
     for s in args.sizes.split(","):
         h, w = (int(v) for v in s.split("x"))
         imgs = np.stack([natural_image(h, w, 4242 + i) for i in range(args.batch)])
+        if args.pinned:
+            import torch
+            keep = torch.from_numpy(imgs).pin_memory()
+            imgs = keep.numpy()
         eng = ak.Engine(device=0, max_width=w, max_height=h, max_batch=args.batch)
         for _ in range(5):
             f = eng.extract_batch_u8(imgs)
